@@ -1,0 +1,84 @@
+// Library-level entry points, error plumbing, TMA descriptor construction.
+#include <stdio.h>
+#include <string.h>
+#include "internal.h"
+
+namespace sres {
+
+static thread_local char t_err[512] = "";
+
+int set_error(int code, const char* msg) {
+  snprintf(t_err, sizeof(t_err), "%s", msg ? msg : "");
+  return code;
+}
+int set_cuda_error(cudaError_t e, const char* where) {
+  snprintf(t_err, sizeof(t_err), "%s: %s (%s)", where, cudaGetErrorString(e), cudaGetErrorName(e));
+  return SRES_ERR_CUDA;
+}
+
+int device_sm_count() {
+  static thread_local int cached_dev = -1, cached_sms = 0;
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  if (dev != cached_dev) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+      cudaGetLastError();
+      return -1;
+    }
+    cached_dev = dev;
+    cached_sms = sms;
+  }
+  return cached_sms;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+int make_tmap_rows64(CUtensorMap* out, const void* base, uint64_t nrows, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(SRES_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(base) & 127) != 0)
+    return set_error(SRES_ERR_INVALID_ARG, "TMA operand must be 128-byte aligned");
+  cuuint64_t dims[2] = {64, nrows};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[128];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (CUresult %d, rows %llu, box %u)", (int)r,
+             (unsigned long long)nrows, box_rows);
+    return set_error(SRES_ERR_CUDA, msg);
+  }
+  return SRES_OK;
+}
+
+}  // namespace sres
+
+extern "C" int sres_abi_version(void) { return 1; }
+extern "C" const char* sres_last_error(void) { return sres::t_err; }
+extern "C" int sres_device_sm_count(void) { return sres::device_sm_count(); }
+extern "C" int64_t sres_ptl_rows(int B, int H, int W) { return (int64_t)B * (H + 1) * (W + 1); }

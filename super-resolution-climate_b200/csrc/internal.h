@@ -1,0 +1,27 @@
+// Host-side helpers shared by the translation units of libsres_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/sres_b200.h"
+
+namespace sres {
+
+// thread-local last-error text + status passthrough
+int set_error(int code, const char* msg);
+int set_cuda_error(cudaError_t e, const char* where);
+
+// cached SM count of the current device (<=0 when there is none)
+int device_sm_count();
+
+// 2-D TMA descriptor over a row-major [nrows][64] bf16 matrix (128-byte rows), box = 64 x box_rows,
+// 128B swizzle, zero fill outside [0, nrows).
+int make_tmap_rows64(CUtensorMap* out, const void* base, uint64_t nrows, uint32_t box_rows);
+
+#define SRES_CHECK_LAUNCH(where)                                  \
+  do {                                                            \
+    cudaError_t e__ = cudaGetLastError();                         \
+    if (e__ != cudaSuccess) return sres::set_cuda_error(e__, where); \
+  } while (0)
+
+}  // namespace sres
