@@ -101,6 +101,20 @@ SRES_API int sres_conv3x3_igemm(const sres_conv_args* args, void* stream);
 SRES_API int sres_pack_conv_weights(const float* w_oihw, void* out_bf16, int mode, int n_rows, int cin,
                            int cout_total, int oc_stride, int oc_offset, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* 3x3 convolution weight + bias gradient (split-K tcgen05 GEMM + deterministic reduce)       */
+/* replaces the grad_weight / grad_bias outputs of aten::convolution_backward for the same    */
+/* nn.Conv2d modules, reached from mloss.backward() (sres/controller/dual_trainer.py:322).     */
+/*   x_bf16  [rows][64] bf16 PTL, the conv input;  dy_bf16 [rows][64] bf16 PTL, grad of output */
+/*   dw_oihw fp32 (cout_total, 64, 3, 3); channel n of dy maps to oc = n*oc_stride+oc_offset   */
+/*   dbias   fp32 (cout_total) or NULL;  accumulate != 0 adds into dw/dbias instead of storing */
+/*   workspace: at least sres_conv_wgrad_workspace_bytes() bytes of device memory              */
+/* ------------------------------------------------------------------------------------------ */
+SRES_API size_t sres_conv_wgrad_workspace_bytes(void);
+SRES_API int sres_conv3x3_wgrad(const void* x_bf16, const void* dy_bf16, int B, int H, int W, float* dw_oihw,
+                                float* dbias, int cout_total, int oc_stride, int oc_offset, int accumulate,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

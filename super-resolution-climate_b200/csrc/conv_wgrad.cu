@@ -1,0 +1,244 @@
+// Weight gradient of the 3x3 / 64-feature convolution as a split-K tcgen05 GEMM (sm_100a).
+//
+//   dW[tap][ci][co] = sum_q  X[q + off(tap)][ci] * dY[q][co]          q = PTL row (the K dimension)
+//
+// Both operands are "MN-major": a shared-memory row is one K index (position) holding 64 contiguous
+// channels -- exactly the PTL row the TMA loads.  Two taps are stacked on the UMMA M dimension
+// (M = 128 = 2 x 64 ci): the second group of 64 rows is the SAME halo window shifted by
+// (off_b - off_a) rows, expressed through the descriptor's leading-dimension byte offset.  9 taps
+// -> 5 accumulators of 128 x 64 fp32 in TMEM (the last one carries one junk half).
+//
+// Each persistent CTA reduces its share of 128-position chunks and writes one fp32 partial
+// [5][128][64] (+ the bias-gradient partial, column sums of dY).  A second kernel sums the
+// partials in a fixed order (deterministic) and scatters them into the OIHW fp32 gradient.
+//
+// Replaces the weight/bias part of aten::convolution_backward for the reference's nn.Conv2d
+// (sres/model/common/cnn.py:8-9), reached from mloss.backward() (dual_trainer.py:322).
+#include "ptx.cuh"
+#include "internal.h"
+
+namespace sres {
+
+constexpr int kWgMaxStages = 4;
+constexpr int kWgAcc = 5;
+
+struct WgradKParams {
+  int P, npos, n_chunks, nstage, xrows;
+  int off_a[kWgAcc];   // row offset (ky*P+kx) of the first tap of each accumulator
+  int lbo[kWgAcc];     // byte distance to the second tap's window
+  float* part;         // [grid][5*128*64 + 64]
+};
+
+__global__ void __launch_bounds__(256, 1)
+conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                     const WgradKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = (128 + p.xrows) * 128;
+  uint8_t* tail = smem + p.nstage * stage_bytes;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* bar_empty = bar_full + kWgMaxStages;
+  uint64_t* bar_done = bar_empty + kWgMaxStages;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_done + 1);
+  float* s_db = reinterpret_cast<float*>(tmem_holder + 2);  // [4][64]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    for (int i = 0; i < kWgMaxStages; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1 + 4);  // MMA commit + 4 bias-gradient warps
+    }
+    mbar_init(bar_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_holder, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x, ++it) {
+        const int slot = it % p.nstage;
+        const uint32_t ph = (it / p.nstage) & 1;
+        mbar_wait(&bar_empty[slot], ph ^ 1, 11);
+        mbar_expect_tx(&bar_full[slot], stage_bytes);
+        uint8_t* dst = smem + slot * stage_bytes;
+        const int q0 = c * 128;
+        tma_load_2d(dst, &tmDY, &bar_full[slot], 0, q0);
+        tma_load_2d(dst + 64 * 128, &tmDY, &bar_full[slot], 0, q0 + 64);
+        uint8_t* xdst = dst + 128 * 128;
+        const int x0 = q0 - (p.P + 1);
+        for (int r = 0; r < p.xrows; r += 64) tma_load_2d(xdst + r * 128, &tmX, &bar_full[slot], 0, x0 + r);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+      const uint32_t s_addr = smem_u32(smem);
+      int it = 0;
+      for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x, ++it) {
+        const int slot = it % p.nstage;
+        const uint32_t ph = (it / p.nstage) & 1;
+        mbar_wait(&bar_full[slot], ph, 12);
+        tc_fence_after();
+        const uint32_t dy_addr = s_addr + slot * stage_bytes;
+        const uint32_t x_addr = dy_addr + 128 * 128;
+#pragma unroll
+        for (int a = 0; a < kWgAcc; ++a) {
+          const uint32_t xa = x_addr + uint32_t(p.off_a[a]) * 128;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t da = make_sdesc_sw128(xa + kk * 2048, uint32_t(p.lbo[a]), 1024, 0);
+            const uint64_t db = make_sdesc_sw128(dy_addr + kk * 2048, 1024, 1024, 0);
+            umma_bf16(tmem_base + a * 64, da, db, idesc, (it | kk) ? 1u : 0u);
+          }
+        }
+        umma_commit(&bar_empty[slot]);
+      }
+      umma_commit(bar_done);
+    }
+  } else if (warp >= 4) {
+    // bias gradient: column sums of the dY tile, read straight from the swizzled smem rows.
+    const int wq = warp & 3;
+    float acc0 = 0.f, acc1 = 0.f;  // channels 2*lane, 2*lane+1 over rows wq*32 .. wq*32+31
+    int it = 0;
+    for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x, ++it) {
+      const int slot = it % p.nstage;
+      const uint32_t ph = (it / p.nstage) & 1;
+      mbar_wait(&bar_full[slot], ph, 13);
+      const uint8_t* dy = smem + slot * stage_bytes;
+      const int chunk = lane >> 2, within = (lane & 3) * 4;
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const int row = wq * 32 + r;
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(dy + row * 128 + ((chunk ^ (row & 7)) << 4) + within);
+        acc0 += bf16_lo(v);
+        acc1 += bf16_hi(v);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_empty[slot]);
+    }
+    s_db[wq * 64 + 2 * lane] = acc0;
+    s_db[wq * 64 + 2 * lane + 1] = acc1;
+    // drain the accumulators
+    mbar_wait(bar_done, 0, 14);
+    tc_fence_after();
+    float* out = p.part + (size_t)blockIdx.x * (kWgAcc * 128 * 64 + 64);
+    const int m = wq * 32 + lane;
+    for (int a = 0; a < kWgAcc; ++a) {
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t raw[16];
+        tmem_ld16(tmem_base + (uint32_t(wq * 32) << 16) + a * 64 + ch * 16, raw);
+        tmem_ld_wait();
+        float4* op = reinterpret_cast<float4*>(out + ((size_t)a * 128 + m) * 64 + ch * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          op[j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                              __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float* out = p.part + (size_t)blockIdx.x * (kWgAcc * 128 * 64 + 64) + kWgAcc * 128 * 64;
+    out[threadIdx.x] = s_db[threadIdx.x] + s_db[64 + threadIdx.x] + s_db[128 + threadIdx.x] + s_db[192 + threadIdx.x];
+  }
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// Sum the per-CTA partials in CTA order and scatter into the OIHW gradient.
+//   accumulator a, row m = half*64 + ci, column n = co   ->  tap = 2a + half (a < 4), tap 8 for a == 4 half 0
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int nparts, float* __restrict__ dw,
+                                    float* __restrict__ db, int cout_total, int oc_stride, int oc_offset,
+                                    int accumulate) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = kWgAcc * 128 * 64 + 64;
+  if (idx >= stride) return;
+  float s = 0.f;
+  for (int i = 0; i < nparts; ++i) s += part[(size_t)i * stride + idx];
+  if (idx >= kWgAcc * 128 * 64) {
+    const int co = idx - kWgAcc * 128 * 64;
+    const int oc = co * oc_stride + oc_offset;
+    if (db && oc < cout_total) db[oc] = accumulate ? db[oc] + s : s;
+    return;
+  }
+  const int n = idx & 63;
+  const int m = (idx >> 6) & 127;
+  const int a = idx >> 13;
+  const int half = m >> 6, ci = m & 63;
+  const int tap = 2 * a + half;
+  if (tap > 8) return;
+  const int oc = n * oc_stride + oc_offset;
+  if (oc >= cout_total) return;
+  float* o = dw + ((size_t)oc * 64 + ci) * 9 + tap;
+  *o = accumulate ? *o + s : s;
+}
+
+}  // namespace sres
+
+extern "C" size_t sres_conv_wgrad_workspace_bytes(void) {
+  int sms = sres::device_sm_count();
+  if (sms <= 0) sms = 148;
+  return (size_t)sms * (sres::kWgAcc * 128 * 64 + 64) * sizeof(float);
+}
+
+extern "C" int sres_conv3x3_wgrad(const void* x_bf16, const void* dy_bf16, int B, int H, int W, float* dw_oihw,
+                                  float* dbias, int cout_total, int oc_stride, int oc_offset, int accumulate,
+                                  void* workspace, size_t workspace_bytes, void* stream_) {
+  using namespace sres;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!x_bf16 || !dy_bf16 || !dw_oihw || !workspace) return set_error(SRES_ERR_INVALID_ARG, "wgrad: null pointer");
+  if (B <= 0 || H <= 0 || W <= 0) return set_error(SRES_ERR_INVALID_ARG, "wgrad: bad geometry");
+  WgradKParams p{};
+  p.P = W + 1;
+  const long long npos = (long long)B * (H + 1) * (W + 1);
+  if (npos > 0x7fffff00LL) return set_error(SRES_ERR_UNSUPPORTED, "wgrad: batch too large");
+  p.npos = (int)npos;
+  p.n_chunks = (p.npos + 127) / 128;
+  p.xrows = (128 + 2 * (p.P + 1) + 1 + 63) / 64 * 64;
+  const int stage_bytes = (128 + p.xrows) * 128;
+  int nstage = (232448 - 1024 - 2048) / stage_bytes;
+  if (nstage > kWgMaxStages) nstage = kWgMaxStages;
+  if (nstage < 1) return set_error(SRES_ERR_UNSUPPORTED, "wgrad: image too wide for the flat halo window");
+  p.nstage = nstage;
+  for (int a = 0; a < kWgAcc; ++a) {
+    const int ta = 2 * a, tb = (2 * a + 1 <= 8) ? 2 * a + 1 : -1;
+    const int offa = (ta / 3) * p.P + (ta % 3);
+    p.off_a[a] = offa;
+    p.lbo[a] = tb >= 0 ? (((tb / 3) * p.P + (tb % 3)) - offa) * 128 : 128;
+    if (p.lbo[a] >= (1 << 18)) return set_error(SRES_ERR_UNSUPPORTED, "wgrad: tap distance exceeds descriptor range");
+  }
+  int sms = device_sm_count();
+  if (sms <= 0) return set_error(SRES_ERR_NO_DEVICE, "wgrad: no CUDA device");
+  const int grid = p.n_chunks < sms ? p.n_chunks : sms;
+  const size_t need = (size_t)grid * (kWgAcc * 128 * 64 + 64) * sizeof(float);
+  if (workspace_bytes < need) return set_error(SRES_ERR_INVALID_ARG, "wgrad: workspace too small");
+  p.part = (float*)workspace;
+  CUtensorMap tmX, tmDY;
+  int rc = make_tmap_rows64(&tmX, x_bf16, (uint64_t)p.npos, 64);
+  if (rc) return rc;
+  rc = make_tmap_rows64(&tmDY, dy_bf16, (uint64_t)p.npos, 64);
+  if (rc) return rc;
+  const size_t smem = (size_t)nstage * stage_bytes + 1024 + 2048;
+  cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return set_cuda_error(e, "wgrad: smem attribute");
+  conv3x3_wgrad_kernel<<<grid, 256, smem, stream>>>(tmX, tmDY, p);
+  SRES_CHECK_LAUNCH("wgrad: launch");
+  const int total = kWgAcc * 128 * 64 + 64;
+  wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(p.part, grid, dw_oihw, dbias, cout_total, oc_stride,
+                                                               oc_offset, accumulate);
+  SRES_CHECK_LAUNCH("wgrad: reduce launch");
+  return SRES_OK;
+}
