@@ -65,14 +65,15 @@ SRES_API int64_t sres_ptl_rows(int B, int H, int W);
 #define SRES_EPI_POOL 2u       /* emit per-tile channel sums for the CA average pool (network.py:35,45) */
 
 #define SRES_MAP_IDENT 0       /* output position == input position                              */
-#define SRES_MAP_SHUFFLE 1     /* PixelShuffle(2) store: (b,y,x) -> (b,2y+sub_i,2x+sub_j) (blocks.py:65) */
-#define SRES_MAP_UNSHUFFLE 2   /* inverse: (b,y,x) -> sub-grid (y&1,x&1), position (b,y/2,x/2)     */
+#define SRES_MAP_SHUFFLE 1     /* PixelShuffle(f) store: (b,y,x) -> (b,f*y+sub_i,f*x+sub_j) (blocks.py:65,70) */
+#define SRES_MAP_UNSHUFFLE 2   /* inverse: (b,y,x) -> sub-grid (y%f,x%f), position (b,y/f,x/f)     */
 
 typedef struct sres_conv_args {
   const void* in_bf16;     /* [rows_in][64] bf16 PTL, geometry (B,H,W)                          */
   const void* wpack_bf16;  /* [9][n_out][64] bf16, tap-major, from sres_pack_conv_weights        */
   const float* bias;       /* [n_out] fp32 or NULL                                              */
   const float* resid_f32;  /* fp32 PTL indexed like the OUTPUT, added before ReLU; may alias out_f32; or NULL */
+  const float* resid2_f32; /* second fp32 PTL addend (group skip gradient), may alias out_f32; or NULL */
   const void* mask_bf16;   /* bf16 PTL indexed like the INPUT: v = mask > 0 ? v : 0 (ReLU backward) or NULL */
   float* out_f32;          /* fp32 PTL output or NULL                                           */
   void* out_bf16;          /* bf16 PTL output or NULL                                           */
@@ -84,7 +85,8 @@ typedef struct sres_conv_args {
   uint32_t epi_flags;      /* SRES_EPI_*                                                        */
   int32_t map_mode;        /* SRES_MAP_*                                                        */
   int32_t sub_i, sub_j;    /* sub-pixel of SRES_MAP_SHUFFLE                                     */
-  int32_t debug_flags;     /* bit0: put (addr>>7)&7 in the UMMA descriptor base_offset field    */
+  int32_t shuffle_factor;  /* PixelShuffle factor of SRES_MAP_(UN)SHUFFLE; 0 means 2             */
+  int32_t debug_flags;     /* bit0: put (addr>>7)&7 in the UMMA descriptor base_offset field (bring-up only) */
 } sres_conv_args;
 
 /* Number of 128-position M tiles of a (B,H,W) batch (size of pool_part's leading dim). */
@@ -114,6 +116,137 @@ SRES_API size_t sres_conv_wgrad_workspace_bytes(void);
 SRES_API int sres_conv3x3_wgrad(const void* x_bf16, const void* dy_bf16, int B, int H, int W, float* dw_oihw,
                                 float* dbias, int cout_total, int oc_stride, int oc_offset, int accumulate,
                                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Narrow 3x3 convolutions at the ends of the network (CUDA cores, HBM-bound)                 */
+/* ------------------------------------------------------------------------------------------ */
+/* planar fp32 (B,Cs,H,W), Cs = 1..4  ->  64-feature PTL rows (fp32 and/or bf16).
+ *   transposed == 0: w (64,Cs,3,3) + bias: the head conv forward (sres/model/rcan/network.py:13,23)
+ *   transposed == 1: w (Cs,64,3,3): input-gradient of the tail conv 64->Cs (network.py:16)
+ *   unshuffle  > 1 : store with PixelUnshuffle(unshuffle) addressing (sub-grid-major PTL)          */
+SRES_API int sres_conv3x3_small_in(const float* in_nchw, const float* w, const float* bias, int B, int Cs, int H,
+                                   int W, int transposed, int unshuffle, float* out_f32, void* out_bf16,
+                                   void* stream);
+SRES_API size_t sres_small_wgrad_workspace_bytes(void);
+/* head conv weight/bias gradient; the output gradient is g1 (+ g2 when not NULL), fp32 PTL      */
+SRES_API int sres_small_in_wgrad(const float* g1_f32, const float* g2_f32, const float* in_nchw, int B, int Cs,
+                                 int H, int W, float* dw, float* db, int accumulate, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+/* tail conv weight/bias gradient from the planar output gradient and the bf16 PTL conv input    */
+SRES_API int sres_small_out_wgrad(const float* dout_nchw, const void* u_bf16, int B, int Cs, int H, int W,
+                                  float* dw, float* db, int accumulate, void* workspace, size_t workspace_bytes,
+                                  void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Channel attention + RCAB residual  (sres/model/rcan/network.py:31-47 CALayer, :61-64 RCAB)  */
+/*   w1 (hidden,64) b1 (hidden) = conv_du.0 ; w2 (64,hidden) b2 (64) = conv_du.2               */
+/* ------------------------------------------------------------------------------------------ */
+SRES_API int sres_ca_blocks_per_image(int B, int H, int W);
+/* per-image channel sums of a bf16 PTL tensor -> pool_sum [B][64] (small images only)          */
+SRES_API int sres_ca_pool(const void* t2_bf16, float* pool_sum, int B, int H, int W, void* stream);
+/* x_out = x_in + t2 * sigmoid(MLP(mean(t2)));  xb_out = bf16(x_out);  saves mean and scale [B][64].
+ * The pooled sums come either from the conv epilogue partials (pool_part) or from pool_sum.      */
+SRES_API int sres_ca_apply_fwd(const void* t2_bf16, const float* pool_part, const float* pool_sum, const float* w1,
+                               const float* b1, const float* w2, const float* b2, int hidden, const float* x_in,
+                               float* x_out, void* xb_out_bf16, float* save_mean, float* save_s, int B, int H, int W,
+                               void* stream);
+/* backward of the above w.r.t. t2: dt2 (bf16 PTL) from the fp32 trunk gradient; saves ds [B][64];
+ * ds_part: scratch [B][sres_ca_blocks_per_image][64] floats                                       */
+SRES_API int sres_ca_bwd(const float* grad_f32, const void* t2_bf16, const float* w1, const float* b1,
+                         const float* w2, const float* b2, int hidden, const float* save_mean, float* ds_part,
+                         void* dt2_bf16, float* save_ds, int B, int H, int W, void* stream);
+/* parameter gradients of `nlayers` CALayers whose parameters sit layer_stride floats apart       */
+SRES_API int sres_ca_param_grads(const float* params_first, float* grads_first, int64_t layer_stride, int nlayers,
+                                 const float* save_mean, const float* save_ds, int B, int hidden, int accumulate,
+                                 void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Bicubic resize = F.interpolate(mode="bicubic", align_corners=False)                         */
+/*   sres/base/util/array.py:72-76 (downsample, scale = s) and :84-87 (upsample, scale = 1/s)  */
+/* ------------------------------------------------------------------------------------------ */
+SRES_API int sres_bicubic_resize(const float* in, float* out, int planes, int Hi, int Wi, int Ho, int Wo,
+                                 double scale_h, double scale_w, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Losses: kind 0 = l2 / RMSE (sres/controller/stats.py:5-8), 1 = charbonnier                  */
+/* (sres/controller/dual_trainer.py:196-198), 2 = l1 (BASELINE north_star variant).            */
+/* The target plane (tH,tW) may exceed the product's (H,W): conform_to_product,                */
+/* dual_trainer.py:200-203.  stat: device double[2]; stat[0] = sum_i f(d_i) of THIS rank --    */
+/* a data-parallel caller all-reduces stat[0] before sres_loss_value.           */
+/* ------------------------------------------------------------------------------------------ */
+SRES_API size_t sres_loss_workspace_bytes(void);
+SRES_API int sres_loss_sum(const float* prd, const float* tgt, int planes, int H, int W, int tH, int tW, int kind,
+                           double* stat, void* workspace, size_t workspace_bytes, void* stream);
+SRES_API int sres_loss_value(const double* stat, double n_total, int kind, float* loss, void* stream);
+SRES_API int sres_loss_grad(const float* prd, const float* tgt, int planes, int H, int W, int tH, int tW, int kind,
+                            const float* loss, double n_total, float gscale, const float* gscale_dev, float* grad,
+                            void* stream); /* upstream factor = gscale * (gscale_dev ? *gscale_dev : 1) */
+
+/* ------------------------------------------------------------------------------------------ */
+/* Fused Adam over flat fp32 buffers = torch.optim.Adam(lr, betas, eps, weight_decay).step()   */
+/*   sres/controller/dual_trainer.py:126, :323.  n % 4 == 0, 16-byte aligned.                  */
+/* ------------------------------------------------------------------------------------------ */
+SRES_API int sres_adam_step_flat(float* p, const float* g, float* m, float* v, int64_t n, int64_t step, double lr,
+                                 double beta1, double beta2, double eps, double weight_decay, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Whole network: RCAN forward / backward  (sres/model/rcan/network.py:9-27)                   */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct sres_rcan_desc {
+  int32_t B, H, W;         /* low-resolution tile batch                                         */
+  int32_t cin, cout;       /* image channels (nchannels_in / nchannels_out, manager.py:52)       */
+  int32_t nfeatures;       /* 64                                                                 */
+  int32_t n_groups;        /* nlayers  (residual groups)                                         */
+  int32_t n_blocks;        /* nblocks  (RCABs per group)                                         */
+  int32_t reduction;       /* cbottleneck                                                        */
+  int32_t n_up;            /* upsampler stages                                                   */
+  int32_t up_factor[4];    /* PixelShuffle factor of each stage: 2,2 for x4; 3 for x3            */
+} sres_rcan_desc;
+
+/* Parameters / gradients are ONE flat fp32 buffer in the reference's state_dict order.        */
+SRES_API int64_t sres_rcan_param_count(const sres_rcan_desc* d);
+/* Workspace size.  The workspace must be zero-filled once before first use (padding rows of the
+ * PixelUnshuffle-layout gradient buffers are never written) and must persist from forward to
+ * backward in training mode.                                                                   */
+SRES_API int sres_rcan_workspace_bytes(const sres_rcan_desc* d, int training, size_t* bytes);
+/* Re-derive the bf16 tensor-core operands from the fp32 parameters (after every update).       */
+SRES_API int sres_rcan_pack_weights(const sres_rcan_desc* d, const float* params, void* workspace, int training,
+                                    void* stream);
+/* x (B,cin,H,W) fp32 -> out (B,cout,H*s,W*s) fp32.  training != 0 keeps activations for backward. */
+SRES_API int sres_rcan_forward(const sres_rcan_desc* d, const float* params, const float* x_nchw, float* out_nchw,
+                               void* workspace, int training, void* stream);
+/* Backward in segments [seg_begin, seg_end): 0 = tail + upsampler + body-tail conv,
+ * 1..G = residual groups G-1..0, G+1 = head conv.  Each segment completes the gradients of the
+ * parameter range reported by sres_rcan_segment_params, so a data-parallel caller can start
+ * the all-reduce of that range while the next segment runs.                                     */
+SRES_API int sres_rcan_num_segments(const sres_rcan_desc* d);
+SRES_API int sres_rcan_segment_params(const sres_rcan_desc* d, int seg, int64_t* offset, int64_t* count);
+SRES_API int sres_rcan_backward(const sres_rcan_desc* d, const float* params, const float* x_nchw,
+                                const float* dout_nchw, float* grads, int accumulate, void* workspace, int seg_begin,
+                                int seg_end, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Tile extraction / normalisation / stitching (index-exact data movement around the model)   */
+/*   region (C,Y,X) fp32; tile grid gy x gx of T x T tiles starting at (y0,x0)                 */
+/*   (sres/data/tiles.py:110-127).  A "candidate" tile index is c*gy*gx + ty*gx + tx.          */
+/* ------------------------------------------------------------------------------------------ */
+/* flags[cand] = 1 when every element of the candidate tile is finite -- the survivors of the
+ * reference's NaN-tile drop, isfinite(tile.mean(-1).mean(-1)) (sres/base/source/swot/raw.py:226) */
+SRES_API int sres_tiles_finite_flags(const float* region, int C, int Y, int X, int y0, int x0, int T, int gy, int gx,
+                                     int32_t* flags, void* stream);
+/* out[slot] (T x T) = candidate tile src_tile[slot]; slot = n*C + c of the (N,C,T,T) result
+ * (raw.py:216-233; the table encodes the reference's channel-major order or the corrected one)  */
+SRES_API int sres_tiles_gather(const float* region, int C, int Y, int X, int y0, int x0, int T, int gy, int gx,
+                               const int32_t* src_tile, int nslots, float* out, void* stream);
+/* per plane (x-mean)/std, NaN-skipping, population std (raw.py:176-183), with the xyflip
+ * orientation flip_index = 0..7 (bit0 flip x, bit1 flip y, bit2 transpose; source/batch.py:37-49)
+ * fused into the store; mean/std [nplanes] are returned for denorm                               */
+SRES_API int sres_tiles_lnorm(const float* in, int nplanes, int T, int flip_index, float* out, float* mean,
+                              float* std_, void* stream);
+/* image (gy*t, gx*t) of variable ivar: tile cell_to_tile[cy*gx+cx] (or NaN when < 0), optionally
+ * de-normalised x*std+mean (sres/controller/dual_trainer.py:449-480 assemble_images, :67-77 denorm) */
+SRES_API int sres_tiles_stitch(const float* tiles, int C, int ivar, int t, int gy, int gx, const int32_t* cell_to_tile,
+                               const float* mean, const float* std_, float* out, void* stream);
 
 #ifdef __cplusplus
 }

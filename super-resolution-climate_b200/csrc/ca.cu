@@ -1,0 +1,352 @@
+// Channel attention (CALayer) + RCAB residual, forward and backward, on the padded tile layout.
+// Memory-bound: every kernel touches each 64-channel row with 16/32-byte vector accesses, one
+// 8-channel slice per thread, and the tiny squeeze-excite MLP is recomputed per block.
+//
+// Reference: sres/model/rcan/network.py:31-47 (CALayer: AdaptiveAvgPool2d(1) -> 1x1 conv F->F/r ->
+// ReLU -> 1x1 conv F/r->F -> Sigmoid -> x*y) and :61-64 (RCAB: res = body(x); res += x).
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace sres {
+
+constexpr int kCaThreads = 256;
+constexpr int kCaMaxHidden = 64;
+
+struct CaGeom {
+  int B, H, W, P, RP;   // RP = (H+1)*(W+1)
+  int hid;              // F / reduction
+  int blocks_per_image;
+};
+
+// ---- shared: s = sigmoid(W2 relu(W1 m + b1) + b2) for one image -----------------------------
+// sm_m[64] must hold the pooled means.  Fills sm_h[hid], sm_s[64].  All 256 threads call.
+__device__ __forceinline__ void ca_mlp(const float* __restrict__ w1, const float* __restrict__ b1,
+                                       const float* __restrict__ w2, const float* __restrict__ b2, int hid,
+                                       const float* sm_m, float* sm_h, float* sm_z, float* sm_s) {
+  const int tid = threadIdx.x;
+  if (tid < hid) {
+    float a = b1[tid];
+    for (int c = 0; c < 64; ++c) a = fmaf(w1[tid * 64 + c], sm_m[c], a);
+    sm_h[tid] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  if (tid < 64) {
+    float a = b2[tid];
+    for (int j = 0; j < hid; ++j) a = fmaf(w2[tid * hid + j], sm_h[j], a);
+    sm_z[tid] = a;
+    sm_s[tid] = 1.f / (1.f + expf(-a));
+  }
+  __syncthreads();
+}
+
+// ---- stand-alone average-pool sums (used when an image is smaller than one 128-row M tile, where
+// the conv epilogue's two-segment partials do not apply) --------------------------------------
+__global__ void __launch_bounds__(kCaThreads)
+ca_pool_kernel(CaGeom g, const uint16_t* __restrict__ t2, float* __restrict__ pool_sum) {
+  __shared__ float sm[kCaThreads / 8][64 + 1];
+  const int b = blockIdx.x, tid = threadIdx.x, cg = tid & 7;
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int r = tid >> 3; r < g.RP; r += kCaThreads / 8) {
+    const uint4 tv = *reinterpret_cast<const uint4*>(t2 + ((size_t)b * g.RP + r) * 64 + cg * 8);
+    a[0] += bf16_lo(tv.x); a[1] += bf16_hi(tv.x); a[2] += bf16_lo(tv.y); a[3] += bf16_hi(tv.y);
+    a[4] += bf16_lo(tv.z); a[5] += bf16_hi(tv.z); a[6] += bf16_lo(tv.w); a[7] += bf16_hi(tv.w);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[tid >> 3][cg * 8 + j] = a[j];
+  __syncthreads();
+  if (tid < 64) {
+    float s = 0.f;
+    for (int i = 0; i < kCaThreads / 8; ++i) s += sm[i][tid];
+    pool_sum[b * 64 + tid] = s;
+  }
+}
+
+// ---- forward --------------------------------------------------------------------------------
+// x_out = x_in + t2 * s ;  xb_out = bf16(x_out) ; block 0 of each image stores mean and s.
+__global__ void __launch_bounds__(kCaThreads)
+ca_apply_fwd_kernel(CaGeom g, const uint16_t* __restrict__ t2, const float* __restrict__ pool_part,
+                    const float* __restrict__ pool_sum, const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                    const float* __restrict__ b2, const float* x_in, float* x_out, uint16_t* __restrict__ xb_out,
+                    float* __restrict__ save_mean, float* __restrict__ save_s) {
+  __shared__ float sm_red[4][64];
+  __shared__ float sm_m[64], sm_h[kCaMaxHidden], sm_z[64], sm_s[64];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  // pooled mean from the conv epilogue partials: tiles covering rows [b*RP, (b+1)*RP)
+  if (pool_sum) {
+    sm_red[tid >> 6][tid & 63] = (tid < 64) ? pool_sum[b * 64 + tid] : 0.f;
+  } else {
+    const int c = tid & 63, part = tid >> 6;  // 4 partial sums per channel
+    const int t0 = (b * g.RP) / 128, t1 = ((b + 1) * g.RP - 1) / 128;
+    float a = 0.f;
+    for (int t = t0; t <= t1; ++t) {
+      const int seg = b - (t * 128) / g.RP;  // 0 or 1
+      a += pool_part[(((size_t)t * 2 + seg) * 4 + part) * 64 + c];
+    }
+    sm_red[part][c] = a;
+  }
+  __syncthreads();
+  if (tid < 64) sm_m[tid] = (sm_red[0][tid] + sm_red[1][tid] + sm_red[2][tid] + sm_red[3][tid]) / float(g.H * g.W);
+  __syncthreads();
+  ca_mlp(w1, b1, w2, b2, g.hid, sm_m, sm_h, sm_z, sm_s);
+  if (blockIdx.x == 0 && tid < 64) {
+    save_mean[b * 64 + tid] = sm_m[tid];
+    save_s[b * 64 + tid] = sm_s[tid];
+  }
+  const int cg = tid & 7;  // 8-channel slice
+  float s8[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s8[j] = sm_s[cg * 8 + j];
+  const int per_blk = (g.RP + g.blocks_per_image - 1) / g.blocks_per_image;
+  const int r0 = blockIdx.x * per_blk, r1 = min(g.RP, r0 + per_blk);
+  for (int r = r0 + (tid >> 3); r < r1; r += kCaThreads / 8) {
+    const size_t q = (size_t)b * g.RP + r;
+    const uint4 tv = *reinterpret_cast<const uint4*>(t2 + q * 64 + cg * 8);
+    const float4 xa = *reinterpret_cast<const float4*>(x_in + q * 64 + cg * 8);
+    const float4 xb = *reinterpret_cast<const float4*>(x_in + q * 64 + cg * 8 + 4);
+    float o[8];
+    o[0] = fmaf(bf16_lo(tv.x), s8[0], xa.x); o[1] = fmaf(bf16_hi(tv.x), s8[1], xa.y);
+    o[2] = fmaf(bf16_lo(tv.y), s8[2], xa.z); o[3] = fmaf(bf16_hi(tv.y), s8[3], xa.w);
+    o[4] = fmaf(bf16_lo(tv.z), s8[4], xb.x); o[5] = fmaf(bf16_hi(tv.z), s8[5], xb.y);
+    o[6] = fmaf(bf16_lo(tv.w), s8[6], xb.z); o[7] = fmaf(bf16_hi(tv.w), s8[7], xb.w);
+    *reinterpret_cast<float4*>(x_out + q * 64 + cg * 8) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(x_out + q * 64 + cg * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    if (xb_out)
+      *reinterpret_cast<uint4*>(xb_out + q * 64 + cg * 8) =
+          make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+  }
+}
+
+// ---- backward, pass 1: ds[b][c] partials = sum_q g[q][c] * t2[q][c] --------------------------
+__global__ void __launch_bounds__(kCaThreads)
+ca_bwd_reduce_kernel(CaGeom g, const float* __restrict__ grad, const uint16_t* __restrict__ t2,
+                     float* __restrict__ ds_part) {
+  __shared__ float sm[kCaThreads / 8][64 + 1];
+  const int b = blockIdx.y, tid = threadIdx.x, cg = tid & 7;
+  const int per_blk = (g.RP + g.blocks_per_image - 1) / g.blocks_per_image;
+  const int r0 = blockIdx.x * per_blk, r1 = min(g.RP, r0 + per_blk);
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int r = r0 + (tid >> 3); r < r1; r += kCaThreads / 8) {
+    const size_t q = (size_t)b * g.RP + r;
+    const uint4 tv = *reinterpret_cast<const uint4*>(t2 + q * 64 + cg * 8);
+    const float4 ga = *reinterpret_cast<const float4*>(grad + q * 64 + cg * 8);
+    const float4 gb = *reinterpret_cast<const float4*>(grad + q * 64 + cg * 8 + 4);
+    a[0] = fmaf(ga.x, bf16_lo(tv.x), a[0]); a[1] = fmaf(ga.y, bf16_hi(tv.x), a[1]);
+    a[2] = fmaf(ga.z, bf16_lo(tv.y), a[2]); a[3] = fmaf(ga.w, bf16_hi(tv.y), a[3]);
+    a[4] = fmaf(gb.x, bf16_lo(tv.z), a[4]); a[5] = fmaf(gb.y, bf16_hi(tv.z), a[5]);
+    a[6] = fmaf(gb.z, bf16_lo(tv.w), a[6]); a[7] = fmaf(gb.w, bf16_hi(tv.w), a[7]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[tid >> 3][cg * 8 + j] = a[j];
+  __syncthreads();
+  if (tid < 64) {
+    float s = 0.f;
+    for (int i = 0; i < kCaThreads / 8; ++i) s += sm[i][tid];
+    ds_part[((size_t)b * g.blocks_per_image + blockIdx.x) * 64 + tid] = s;
+  }
+}
+
+// ---- backward, pass 2: dt2 = g*s + dm/(H*W) (bf16), padding rows stay 0 ----------------------
+__global__ void __launch_bounds__(kCaThreads)
+ca_bwd_apply_kernel(CaGeom g, const float* __restrict__ grad, const float* __restrict__ ds_part,
+                    const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                    const float* __restrict__ b2, const float* __restrict__ save_mean,
+                    uint16_t* __restrict__ dt2, float* __restrict__ save_ds) {
+  __shared__ float sm_m[64], sm_h[kCaMaxHidden], sm_z[64], sm_s[64], sm_dz[64], sm_dh[kCaMaxHidden], sm_dm[64];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  if (tid < 64) sm_m[tid] = save_mean[b * 64 + tid];
+  __syncthreads();
+  ca_mlp(w1, b1, w2, b2, g.hid, sm_m, sm_h, sm_z, sm_s);
+  if (tid < 64) {
+    float ds = 0.f;
+    for (int i = 0; i < g.blocks_per_image; ++i) ds += ds_part[((size_t)b * g.blocks_per_image + i) * 64 + tid];
+    if (blockIdx.x == 0) save_ds[b * 64 + tid] = ds;
+    const float s = sm_s[tid];
+    sm_dz[tid] = ds * s * (1.f - s);
+  }
+  __syncthreads();
+  if (tid < g.hid) {
+    float a = 0.f;
+    for (int c = 0; c < 64; ++c) a = fmaf(w2[c * g.hid + tid], sm_dz[c], a);
+    sm_dh[tid] = sm_h[tid] > 0.f ? a : 0.f;
+  }
+  __syncthreads();
+  if (tid < 64) {
+    float a = 0.f;
+    for (int j = 0; j < g.hid; ++j) a = fmaf(w1[j * 64 + tid], sm_dh[j], a);
+    sm_dm[tid] = a / float(g.H * g.W);
+  }
+  __syncthreads();
+  const int cg = tid & 7;
+  float s8[8], m8[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s8[j] = sm_s[cg * 8 + j]; m8[j] = sm_dm[cg * 8 + j]; }
+  const int per_blk = (g.RP + g.blocks_per_image - 1) / g.blocks_per_image;
+  const int r0 = blockIdx.x * per_blk, r1 = min(g.RP, r0 + per_blk);
+  for (int r = r0 + (tid >> 3); r < r1; r += kCaThreads / 8) {
+    const size_t q = (size_t)b * g.RP + r;
+    const int y = r / g.P, x = r - y * g.P;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (x != g.W && y != g.H) {
+      const float4 ga = *reinterpret_cast<const float4*>(grad + q * 64 + cg * 8);
+      const float4 gb = *reinterpret_cast<const float4*>(grad + q * 64 + cg * 8 + 4);
+      o.x = pack_bf16x2(fmaf(ga.x, s8[0], m8[0]), fmaf(ga.y, s8[1], m8[1]));
+      o.y = pack_bf16x2(fmaf(ga.z, s8[2], m8[2]), fmaf(ga.w, s8[3], m8[3]));
+      o.z = pack_bf16x2(fmaf(gb.x, s8[4], m8[4]), fmaf(gb.y, s8[5], m8[5]));
+      o.w = pack_bf16x2(fmaf(gb.z, s8[6], m8[6]), fmaf(gb.w, s8[7], m8[7]));
+    }
+    *reinterpret_cast<uint4*>(dt2 + q * 64 + cg * 8) = o;
+  }
+}
+
+// ---- backward: parameter gradients of the squeeze-excite MLP, all RCABs in one launch --------
+// One block per CALayer; loops over the batch in a fixed order (deterministic).
+struct CaParamBatch {
+  const float* params;   // first CALayer's conv_du.0.weight
+  float* grads;          // same position in the gradient buffer
+  long long layer_stride;  // floats between consecutive CALayers (one RCAB)
+  const float* mean;     // [njobs][B][64] saved by forward
+  const float* ds;       // [njobs][B][64] saved by backward
+};
+struct CaParamJob {
+  const float *w1, *b1, *w2, *b2;
+  float *dw1, *db1, *dw2, *db2;
+  const float *mean, *ds;
+};
+
+__global__ void __launch_bounds__(kCaThreads)
+ca_param_grad_kernel(const CaParamBatch batch, int B, int hid, int accumulate) {
+  __shared__ float sm_m[64], sm_h[kCaMaxHidden], sm_z[64], sm_s[64], sm_dz[64], sm_dh[kCaMaxHidden];
+  CaParamJob job;
+  {
+    const long long o = (long long)blockIdx.x * batch.layer_stride;
+    job.w1 = batch.params + o;           job.dw1 = batch.grads + o;
+    job.b1 = job.w1 + hid * 64;          job.db1 = job.dw1 + hid * 64;
+    job.w2 = job.b1 + hid;               job.dw2 = job.db1 + hid;
+    job.b2 = job.w2 + 64 * hid;          job.db2 = job.dw2 + 64 * hid;
+    job.mean = batch.mean + (size_t)blockIdx.x * B * 64;
+    job.ds = batch.ds + (size_t)blockIdx.x * B * 64;
+  }
+  const int tid = threadIdx.x;
+  const int n12 = hid * 64;  // elements of each weight matrix
+  float a1[16], a2[16];       // thread owns elements tid, tid+256, ... of dw1 and dw2 (n12 <= 4096)
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a1[i] = a2[i] = 0.f;
+  float ab1 = 0.f, ab2 = 0.f;
+  for (int b = 0; b < B; ++b) {
+    __syncthreads();
+    if (tid < 64) sm_m[tid] = job.mean[b * 64 + tid];
+    __syncthreads();
+    ca_mlp(job.w1, job.b1, job.w2, job.b2, hid, sm_m, sm_h, sm_z, sm_s);
+    if (tid < 64) {
+      const float s = sm_s[tid];
+      sm_dz[tid] = job.ds[b * 64 + tid] * s * (1.f - s);
+    }
+    __syncthreads();
+    if (tid < hid) {
+      float a = 0.f;
+      for (int c = 0; c < 64; ++c) a = fmaf(job.w2[c * hid + tid], sm_dz[c], a);
+      sm_dh[tid] = sm_h[tid] > 0.f ? a : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int e = tid + i * kCaThreads;
+      if (e < n12) {
+        a1[i] = fmaf(sm_dh[e / 64], sm_m[e % 64], a1[i]);   // dw1[j][c] = dh[j] * m[c]
+        a2[i] = fmaf(sm_dz[e / hid], sm_h[e % hid], a2[i]); // dw2[c][j] = dz[c] * h[j]
+      }
+    }
+    if (tid < hid) ab1 += sm_dh[tid];
+    if (tid < 64) ab2 += sm_dz[tid];
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int e = tid + i * kCaThreads;
+    if (e < n12) {
+      job.dw1[e] = accumulate ? job.dw1[e] + a1[i] : a1[i];
+      job.dw2[e] = accumulate ? job.dw2[e] + a2[i] : a2[i];
+    }
+  }
+  if (tid < hid) job.db1[tid] = accumulate ? job.db1[tid] + ab1 : ab1;
+  if (tid < 64) job.db2[tid] = accumulate ? job.db2[tid] + ab2 : ab2;
+}
+
+static int ca_geom(CaGeom* g, int B, int H, int W, int hid) {
+  if (B <= 0 || H <= 0 || W <= 0) return set_error(SRES_ERR_INVALID_ARG, "ca: bad geometry");
+  if (hid < 1 || hid > kCaMaxHidden) return set_error(SRES_ERR_UNSUPPORTED, "ca: hidden width must be 1..64");
+  g->B = B; g->H = H; g->W = W; g->P = W + 1; g->RP = (H + 1) * (W + 1); g->hid = hid;
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  int bpi = (4 * sms + B - 1) / B;            // ~4 blocks per SM in total
+  const int max_bpi = (g->RP + 31) / 32;      // at least one 32-row sweep each
+  if (bpi > max_bpi) bpi = max_bpi;
+  if (bpi < 1) bpi = 1;
+  g->blocks_per_image = bpi;
+  return SRES_OK;
+}
+
+}  // namespace sres
+
+using namespace sres;
+
+extern "C" int sres_ca_blocks_per_image(int B, int H, int W) {
+  CaGeom g;
+  if (ca_geom(&g, B, H, W, 1)) return -1;
+  return g.blocks_per_image;
+}
+
+extern "C" int sres_ca_pool(const void* t2_bf16, float* pool_sum, int B, int H, int W, void* stream) {
+  CaGeom g;
+  int rc = ca_geom(&g, B, H, W, 1);
+  if (rc) return rc;
+  if (!t2_bf16 || !pool_sum) return set_error(SRES_ERR_INVALID_ARG, "ca_pool: null pointer");
+  ca_pool_kernel<<<B, kCaThreads, 0, (cudaStream_t)stream>>>(g, (const uint16_t*)t2_bf16, pool_sum);
+  SRES_CHECK_LAUNCH("ca_pool: launch");
+  return SRES_OK;
+}
+
+extern "C" int sres_ca_apply_fwd(const void* t2_bf16, const float* pool_part, const float* pool_sum, const float* w1, const float* b1,
+                                 const float* w2, const float* b2, int hidden, const float* x_in, float* x_out,
+                                 void* xb_out_bf16, float* save_mean, float* save_s, int B, int H, int W,
+                                 void* stream) {
+  CaGeom g;
+  int rc = ca_geom(&g, B, H, W, hidden);
+  if (rc) return rc;
+  if (!pool_sum && g.RP < 128) return set_error(SRES_ERR_UNSUPPORTED, "ca_apply_fwd: fused pool partials need (H+1)*(W+1) >= 128; pass pool_sum");
+  if (!t2_bf16 || (!pool_part && !pool_sum) || !w1 || !b1 || !w2 || !b2 || !x_in || !x_out || !save_mean || !save_s)
+    return set_error(SRES_ERR_INVALID_ARG, "ca_apply_fwd: null pointer");
+  dim3 grid(g.blocks_per_image, B);
+  ca_apply_fwd_kernel<<<grid, kCaThreads, 0, (cudaStream_t)stream>>>(
+      g, (const uint16_t*)t2_bf16, pool_part, pool_sum, w1, b1, w2, b2, x_in, x_out, (uint16_t*)xb_out_bf16, save_mean, save_s);
+  SRES_CHECK_LAUNCH("ca_apply_fwd: launch");
+  return SRES_OK;
+}
+
+extern "C" int sres_ca_bwd(const float* grad_f32, const void* t2_bf16, const float* w1, const float* b1,
+                           const float* w2, const float* b2, int hidden, const float* save_mean, float* ds_part,
+                           void* dt2_bf16, float* save_ds, int B, int H, int W, void* stream) {
+  CaGeom g;
+  int rc = ca_geom(&g, B, H, W, hidden);
+  if (rc) return rc;
+  if (!grad_f32 || !t2_bf16 || !w1 || !b1 || !w2 || !b2 || !save_mean || !ds_part || !dt2_bf16 || !save_ds)
+    return set_error(SRES_ERR_INVALID_ARG, "ca_bwd: null pointer");
+  dim3 grid(g.blocks_per_image, B);
+  ca_bwd_reduce_kernel<<<grid, kCaThreads, 0, (cudaStream_t)stream>>>(g, grad_f32, (const uint16_t*)t2_bf16, ds_part);
+  SRES_CHECK_LAUNCH("ca_bwd: reduce launch");
+  ca_bwd_apply_kernel<<<grid, kCaThreads, 0, (cudaStream_t)stream>>>(g, grad_f32, ds_part, w1, b1, w2, b2, save_mean,
+                                                                     (uint16_t*)dt2_bf16, save_ds);
+  SRES_CHECK_LAUNCH("ca_bwd: apply launch");
+  return SRES_OK;
+}
+
+extern "C" int sres_ca_param_grads(const float* params_first, float* grads_first, int64_t layer_stride, int nlayers,
+                                   const float* save_mean, const float* save_ds, int B, int hidden, int accumulate,
+                                   void* stream) {
+  if (!params_first || !grads_first || !save_mean || !save_ds || nlayers <= 0)
+    return set_error(SRES_ERR_INVALID_ARG, "ca_param_grads: bad argument");
+  if (hidden < 1 || hidden > kCaMaxHidden) return set_error(SRES_ERR_UNSUPPORTED, "ca: hidden width must be 1..64");
+  CaParamBatch batch{params_first, grads_first, (long long)layer_stride, save_mean, save_ds};
+  ca_param_grad_kernel<<<nlayers, kCaThreads, 0, (cudaStream_t)stream>>>(batch, B, hidden, accumulate);
+  SRES_CHECK_LAUNCH("ca_param_grads: launch");
+  return SRES_OK;
+}

@@ -31,10 +31,11 @@ struct ConvKParams {
   int stage_rows;         // rows per smem stage (multiple of kBoxRows)
   int n_out, c_real;
   unsigned flags;
-  int map_mode, sub_i, sub_j;
+  int map_mode, sub_i, sub_j, sf;
   int debug_flags;
   const float* bias;
   const float* resid;
+  const float* resid2;
   const uint16_t* mask;
   float* out_f32;
   uint16_t* out_bf16;
@@ -212,14 +213,14 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         long long oq = q;
         bool ovalid = inrange;
         if (p.map_mode == SRES_MAP_SHUFFLE) {
-          const int P2 = 2 * p.W + 1, R2 = 2 * p.H + 1;
-          const int oy = 2 * y + p.sub_i, ox = 2 * x + p.sub_j;
+          const int P2 = p.sf * p.W + 1, R2 = p.sf * p.H + 1;
+          const int oy = p.sf * y + p.sub_i, ox = p.sf * x + p.sub_j;
           ovalid = inrange && oy < R2 && ox < P2;
           oq = (long long)b * R2 * P2 + (long long)oy * P2 + ox;
         } else if (p.map_mode == SRES_MAP_UNSHUFFLE) {
-          const int Pl = p.W / 2 + 1, Rl = p.H / 2 + 1;
-          const int sub = (y & 1) * 2 + (x & 1);
-          oq = (long long)sub * p.B * Rl * Pl + (long long)b * Rl * Pl + (long long)(y >> 1) * Pl + (x >> 1);
+          const int Pl = p.W / p.sf + 1, Rl = p.H / p.sf + 1;
+          const int sub = (y % p.sf) * p.sf + (x % p.sf);
+          oq = (long long)sub * p.B * Rl * Pl + (long long)b * Rl * Pl + (long long)(y / p.sf) * Pl + (x / p.sf);
         }
         const int seg = (b != (tile * 128) / RP) ? 1 : 0;
         const uint32_t trow = tmem_base + (uint32_t(wq * 32) << 16) + uint32_t(acc * acc_cols + m * N_OUT);
@@ -233,6 +234,14 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) + s_bias[ch * 16 + j];
           if (p.resid && ovalid) {
             const float4* rp = reinterpret_cast<const float4*>(p.resid + oq * 64 + ch * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4 r = rp[j];
+              v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+            }
+          }
+          if (p.resid2 && ovalid) {
+            const float4* rp = reinterpret_cast<const float4*>(p.resid2 + oq * 64 + ch * 16);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float4 r = rp[j];
@@ -321,8 +330,9 @@ static int launch_conv(const sres_conv_args* a, cudaStream_t stream) {
   if (!a || !a->in_bf16 || !a->wpack_bf16) return set_error(SRES_ERR_INVALID_ARG, "conv: null input");
   if (a->n_out != 64 && a->n_out != 16) return set_error(SRES_ERR_UNSUPPORTED, "conv: n_out must be 64 or 16");
   if (a->B <= 0 || a->H <= 0 || a->W <= 0) return set_error(SRES_ERR_INVALID_ARG, "conv: bad geometry");
-  if (a->map_mode == SRES_MAP_UNSHUFFLE && ((a->H | a->W) & 1))
-    return set_error(SRES_ERR_INVALID_ARG, "conv: unshuffle needs even H, W");
+  const int sf = a->shuffle_factor > 0 ? a->shuffle_factor : 2;
+  if (a->map_mode == SRES_MAP_UNSHUFFLE && (a->H % sf || a->W % sf))
+    return set_error(SRES_ERR_INVALID_ARG, "conv: unshuffle factor must divide H and W");
   if ((a->epi_flags & SRES_EPI_POOL) && !a->pool_part) return set_error(SRES_ERR_INVALID_ARG, "conv: pool_part missing");
 
   ConvKParams p{};
@@ -343,9 +353,9 @@ static int launch_conv(const sres_conv_args* a, cudaStream_t stream) {
   if (nstage < 1) return set_error(SRES_ERR_UNSUPPORTED, "conv: image too wide for the flat halo window");
   p.nstage = nstage;
   p.n_out = a->n_out; p.c_real = a->c_real;
-  p.flags = a->epi_flags; p.map_mode = a->map_mode; p.sub_i = a->sub_i; p.sub_j = a->sub_j;
+  p.flags = a->epi_flags; p.map_mode = a->map_mode; p.sub_i = a->sub_i; p.sub_j = a->sub_j; p.sf = sf;
   p.debug_flags = a->debug_flags;
-  p.bias = a->bias; p.resid = a->resid_f32; p.mask = (const uint16_t*)a->mask_bf16;
+  p.bias = a->bias; p.resid = a->resid_f32; p.resid2 = a->resid2_f32; p.mask = (const uint16_t*)a->mask_bf16;
   p.out_f32 = a->out_f32; p.out_bf16 = (uint16_t*)a->out_bf16; p.pool_part = a->pool_part; p.out_nchw = a->out_nchw;
 
   CUtensorMap tmA, tmW;

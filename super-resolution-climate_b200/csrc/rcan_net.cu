@@ -1,0 +1,446 @@
+// Whole-network executor: enqueues the RCAN forward / backward kernel sequence on one stream from a
+// single C call (no per-layer host round trips, capturable into a CUDA graph -- all buffers live in a
+// caller-provided workspace at offsets computed from the network description only).
+//
+// Network (reference sres/model/rcan/network.py:9-27, blocks.py:58-76):
+//   head conv Cin->64 | G x [ R x RCAB(conv,ReLU,conv,CA,+x) , conv, +x ] | conv, +head | Upsampler | conv 64->Cout
+// Parameters cross the boundary as ONE flat fp32 buffer in state_dict order (the order of
+// `model.state_dict()` of the reference RCAN), gradients likewise.
+//
+// Precision plan (SURVEY.md section 7 "hard parts"): bf16 only where the sole consumer is a
+// tensor-core operand (conv inputs, weights, incoming gradients); the residual trunk, the gradient
+// trunk, pooled statistics, parameter gradients and all accumulation are fp32.
+#include <string.h>
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace sres {
+
+constexpr int kConvW = 64 * 64 * 9;  // floats of one 64->64 conv weight
+
+struct Net {
+  sres_rcan_desc d;
+  int hid;
+  // parameter offsets (floats)
+  long long head_w, head_b, body0, rcab_sz, group_sz, bt_w, bt_b, up_w[4], up_b[4], tail_w, tail_b, n_params;
+  int n_body_convs;
+  // geometry per resolution level
+  int lvH[5], lvW[5];
+  long long lvRows[5];
+  // workspace offsets (bytes)
+  size_t o_wp_fwd, o_wp_dg, o_wp_up_fwd[4], o_wp_up_dg[4], o_wp_tail, o_bias_up[4], o_bias_tail;
+  size_t o_xb, o_t1, o_t2, o_mean, o_s, o_ds, o_resb, o_u[4];
+  size_t o_hf, o_gf[2], o_xf, o_pool_part, o_pool_sum;
+  size_t o_ga, o_gb32, o_gb16, o_dt2, o_dt1, o_ds_part, o_wg_ws, o_sw_ws, o_du16[4], o_du32[4], o_dres32, o_dres16;
+  size_t total;
+  int n_xb, n_t;  // saved-buffer counts (1 in inference mode)
+  long long cidx(int g, int r, int which) const { return (long long)g * (2 * d.n_blocks + 1) + 2 * r + which; }
+  long long cidx_gt(int g) const { return (long long)g * (2 * d.n_blocks + 1) + 2 * d.n_blocks; }
+  long long cidx_bt() const { return (long long)d.n_groups * (2 * d.n_blocks + 1); }
+  long long off_rcab(int g, int r) const { return body0 + g * group_sz + r * rcab_sz; }
+  long long off_gt(int g) const { return body0 + g * group_sz + d.n_blocks * rcab_sz; }
+};
+
+static size_t align_up(size_t v, size_t a = 1024) { return (v + a - 1) / a * a; }
+
+static int build_net(Net* n, const sres_rcan_desc* d, int training) {
+  if (!d) return set_error(SRES_ERR_INVALID_ARG, "rcan: null description");
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0) return set_error(SRES_ERR_INVALID_ARG, "rcan: bad tile geometry");
+  if (d->nfeatures != 64) return set_error(SRES_ERR_UNSUPPORTED, "rcan: kernels are specialised for nfeatures == 64");
+  if (d->cin < 1 || d->cin > 4 || d->cout < 1 || d->cout > 4)
+    return set_error(SRES_ERR_UNSUPPORTED, "rcan: 1..4 image channels supported");
+  if (d->n_groups < 1 || d->n_blocks < 1) return set_error(SRES_ERR_INVALID_ARG, "rcan: need >= 1 group and block");
+  if (d->reduction < 1 || 64 % d->reduction) return set_error(SRES_ERR_INVALID_ARG, "rcan: reduction must divide 64");
+  if (d->n_up < 0 || d->n_up > 4) return set_error(SRES_ERR_UNSUPPORTED, "rcan: at most 4 upsampler stages");
+  memset(n, 0, sizeof(*n));
+  n->d = *d;
+  n->hid = 64 / d->reduction;
+  const int G = d->n_groups, R = d->n_blocks, hid = n->hid;
+  long long o = 0;
+  n->head_w = o; o += 64LL * d->cin * 9;
+  n->head_b = o; o += 64;
+  n->body0 = o;
+  n->rcab_sz = 2LL * (kConvW + 64) + (hid * 64 + hid) + (64 * hid + 64);
+  n->group_sz = R * n->rcab_sz + kConvW + 64;
+  o += G * n->group_sz;
+  n->bt_w = o; o += kConvW;
+  n->bt_b = o; o += 64;
+  n->lvH[0] = d->H; n->lvW[0] = d->W;
+  for (int i = 0; i < d->n_up; ++i) {
+    const int f = d->up_factor[i];
+    if (f != 2 && f != 3) return set_error(SRES_ERR_UNSUPPORTED, "rcan: upsampler stage factor must be 2 or 3");
+    n->up_w[i] = o; o += (long long)f * f * kConvW;
+    n->up_b[i] = o; o += f * f * 64;
+    n->lvH[i + 1] = n->lvH[i] * f; n->lvW[i + 1] = n->lvW[i] * f;
+  }
+  n->tail_w = o; o += (long long)d->cout * 64 * 9;
+  n->tail_b = o; o += d->cout;
+  n->n_params = o;
+  n->n_body_convs = G * (2 * R + 1) + 1;
+  for (int i = 0; i <= d->n_up; ++i) {
+    n->lvRows[i] = (long long)d->B * (n->lvH[i] + 1) * (n->lvW[i] + 1);
+    if (n->lvRows[i] > 0x7fffff00LL) return set_error(SRES_ERR_UNSUPPORTED, "rcan: batch too large");
+  }
+  const size_t r0 = (size_t)n->lvRows[0];
+  const size_t bf = r0 * 128, f32 = r0 * 256;
+  size_t w = 0;
+  auto take = [&](size_t bytes) { size_t at = w; w = align_up(w + bytes); return at; };
+  // packed weights
+  n->o_wp_fwd = take((size_t)n->n_body_convs * kConvW * 2);
+  n->o_wp_dg = take((size_t)n->n_body_convs * kConvW * 2);
+  for (int i = 0; i < d->n_up; ++i) {
+    const int f2 = d->up_factor[i] * d->up_factor[i];
+    n->o_wp_up_fwd[i] = take((size_t)f2 * kConvW * 2);
+    n->o_wp_up_dg[i] = take((size_t)f2 * kConvW * 2);
+    n->o_bias_up[i] = take((size_t)f2 * 64 * 4);
+  }
+  n->o_wp_tail = take(9 * 16 * 64 * 2);
+  n->o_bias_tail = take(16 * 4);
+  // activations
+  n->n_xb = training ? G * (R + 1) + 1 : 2;
+  n->n_t = training ? G * R : 1;
+  n->o_xb = take((size_t)n->n_xb * bf);
+  n->o_t1 = take((size_t)n->n_t * bf);
+  n->o_t2 = take((size_t)n->n_t * bf);
+  n->o_mean = take((size_t)n->n_t * d->B * 64 * 4);
+  n->o_s = take((size_t)n->n_t * d->B * 64 * 4);
+  n->o_resb = take(bf);
+  for (int i = 0; i < d->n_up; ++i) n->o_u[i] = take((size_t)n->lvRows[i + 1] * 128);
+  n->o_hf = take(f32);
+  n->o_gf[0] = take(f32);
+  n->o_gf[1] = take(f32);
+  n->o_xf = take(f32);
+  n->o_pool_part = take((size_t)((r0 + 127) / 128) * 2 * 4 * 64 * 4);
+  n->o_pool_sum = take((size_t)d->B * 64 * 4);
+  if (training) {
+    n->o_ds = take((size_t)n->n_t * d->B * 64 * 4);
+    n->o_ga = take(f32);
+    n->o_gb32 = take(f32);
+    n->o_gb16 = take(bf);
+    n->o_dt2 = take(bf);
+    n->o_dt1 = take(bf);
+    const int bpi = sres_ca_blocks_per_image(d->B, d->H, d->W);
+    n->o_ds_part = take((size_t)d->B * (bpi > 0 ? bpi : 1) * 64 * 4);
+    n->o_wg_ws = take(sres_conv_wgrad_workspace_bytes());
+    n->o_sw_ws = take(sres_small_wgrad_workspace_bytes());
+    for (int i = 0; i < d->n_up; ++i) {
+      // gradient w.r.t. U[i] (level i+1), stored as f*f sub-grids of level-i rows (PixelUnshuffle layout)
+      const int f2 = d->up_factor[i] * d->up_factor[i];
+      n->o_du16[i] = take((size_t)f2 * n->lvRows[i] * 128);
+      n->o_du32[i] = take((size_t)f2 * n->lvRows[i] * 256);
+    }
+    n->o_dres32 = take(f32);
+    n->o_dres16 = take(bf);
+  }
+  n->total = w;
+  return SRES_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bulk weight packing (all 64->64 body convs in one launch; both operand forms)
+// ---------------------------------------------------------------------------------------------
+struct PackBody {
+  const float* params;
+  long long body0, rcab_sz, group_sz, bt_w;
+  int G, R;
+  uint16_t* fwd;
+  uint16_t* dg;
+};
+__global__ void pack_body_kernel(PackBody pb) {
+  const int conv = blockIdx.y;
+  const int per = 2 * pb.R + 1;
+  long long off;
+  if (conv == pb.G * per) off = pb.bt_w;
+  else {
+    const int g = conv / per, k = conv % per;
+    off = pb.body0 + g * pb.group_sz + (k < 2 * pb.R ? (k / 2) * pb.rcab_sz + (k & 1) * (kConvW + 64) : pb.R * pb.rcab_sz);
+  }
+  const float* w = pb.params + off;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < kConvW; idx += gridDim.x * blockDim.x) {
+    const int k = idx & 63, n = (idx >> 6) & 63, t = idx >> 12;
+    const int ky = t / 3, kx = t % 3;
+    const float vf = w[((n * 64 + k) * 3 + ky) * 3 + kx];
+    const float vd = w[((k * 64 + n) * 3 + (2 - ky)) * 3 + (2 - kx)];
+    pb.fwd[(size_t)conv * kConvW + idx] = (uint16_t)(pack_bf16x2(vf, 0.f) & 0xFFFF);
+    pb.dg[(size_t)conv * kConvW + idx] = (uint16_t)(pack_bf16x2(vd, 0.f) & 0xFFFF);
+  }
+}
+__global__ void gather_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int n_out, int stride, int offset,
+                                   int n_src) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_out) {
+    const int s = i * stride + offset;
+    out[i] = s < n_src ? b[s] : 0.f;
+  }
+}
+
+static int pack_all(const Net& n, const float* params, uint8_t* ws, cudaStream_t st) {
+  PackBody pb{params, n.body0, n.rcab_sz, n.group_sz, n.bt_w, n.d.n_groups, n.d.n_blocks,
+              (uint16_t*)(ws + n.o_wp_fwd), (uint16_t*)(ws + n.o_wp_dg)};
+  pack_body_kernel<<<dim3(8, n.n_body_convs), 256, 0, st>>>(pb);
+  SRES_CHECK_LAUNCH("rcan: pack launch");
+  for (int i = 0; i < n.d.n_up; ++i) {
+    const int f = n.d.up_factor[i], f2 = f * f;
+    for (int sub = 0; sub < f2; ++sub) {
+      int rc = sres_pack_conv_weights(params + n.up_w[i], ws + n.o_wp_up_fwd[i] + (size_t)sub * kConvW * 2, 0, 64, 64,
+                                      f2 * 64, f2, sub, st);
+      if (rc) return rc;
+      rc = sres_pack_conv_weights(params + n.up_w[i], ws + n.o_wp_up_dg[i] + (size_t)sub * kConvW * 2, 1, 64, 64,
+                                  f2 * 64, f2, sub, st);
+      if (rc) return rc;
+      gather_bias_kernel<<<1, 64, 0, st>>>(params + n.up_b[i], (float*)(ws + n.o_bias_up[i]) + sub * 64, 64, f2, sub,
+                                           f2 * 64);
+      SRES_CHECK_LAUNCH("rcan: bias gather launch");
+    }
+  }
+  int rc = sres_pack_conv_weights(params + n.tail_w, ws + n.o_wp_tail, 0, 16, 64, n.d.cout, 1, 0, st);
+  if (rc) return rc;
+  gather_bias_kernel<<<1, 64, 0, st>>>(params + n.tail_b, (float*)(ws + n.o_bias_tail), 16, 1, 0, n.d.cout);
+  SRES_CHECK_LAUNCH("rcan: bias gather launch");
+  return SRES_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+static int conv64(const void* in, const void* wp, const float* bias, int B, int H, int W, void* st, float* out_f32,
+                  void* out_bf16, unsigned flags = 0, float* pool = nullptr, const float* resid = nullptr,
+                  const float* resid2 = nullptr, const void* mask = nullptr, int map = SRES_MAP_IDENT, int si = 0,
+                  int sj = 0, int sf = 2) {
+  sres_conv_args a;
+  memset(&a, 0, sizeof(a));
+  a.in_bf16 = in; a.wpack_bf16 = wp; a.bias = bias; a.resid_f32 = resid; a.resid2_f32 = resid2; a.mask_bf16 = mask;
+  a.out_f32 = out_f32; a.out_bf16 = out_bf16; a.pool_part = pool;
+  a.B = B; a.H = H; a.W = W; a.n_out = 64; a.epi_flags = flags; a.map_mode = map; a.sub_i = si; a.sub_j = sj;
+  a.shuffle_factor = sf;
+  return sres_conv3x3_igemm(&a, st);
+}
+
+#define RC(x)            \
+  do {                   \
+    int rc__ = (x);      \
+    if (rc__) return rc__; \
+  } while (0)
+
+static int forward(const Net& n, const float* P, const float* x, float* out, uint8_t* ws, int training, void* st) {
+  const sres_rcan_desc& d = n.d;
+  const int B = d.B, H = d.H, W = d.W, G = d.n_groups, R = d.n_blocks;
+  const size_t bf = (size_t)n.lvRows[0] * 128;
+  const bool fused_pool = (H + 1) * (W + 1) >= 128;
+  auto XB = [&](int i) { return ws + n.o_xb + (size_t)(training ? i : (i & 1)) * bf; };
+  auto T1 = [&](int i) { return ws + n.o_t1 + (size_t)(training ? i : 0) * bf; };
+  auto T2 = [&](int i) { return ws + n.o_t2 + (size_t)(training ? i : 0) * bf; };
+  auto WF = [&](long long c) { return ws + n.o_wp_fwd + (size_t)c * kConvW * 2; };
+  float* hf = (float*)(ws + n.o_hf);
+  float* xf = (float*)(ws + n.o_xf);
+  float* pool_part = (float*)(ws + n.o_pool_part);
+  float* pool_sum = (float*)(ws + n.o_pool_sum);
+  int xbi = 0;  // index of the bf16 copy of the current trunk value
+  RC(sres_conv3x3_small_in(x, P + n.head_w, P + n.head_b, B, d.cin, H, W, 0, 0, hf, XB(0), st));
+  const float* gin = hf;
+  for (int g = 0; g < G; ++g) {
+    float* gout = (float*)(ws + n.o_gf[g & 1]);
+    for (int r = 0; r < R; ++r) {
+      const int ti = g * R + r;
+      const float* pr = P + n.off_rcab(g, r);
+      const float* c1b = pr + kConvW;
+      const float* c2b = pr + 2 * kConvW + 64;
+      const float* w1 = pr + 2 * (kConvW + 64);
+      const float* b1 = w1 + n.hid * 64;
+      const float* w2 = b1 + n.hid;
+      const float* b2 = w2 + 64 * n.hid;
+      RC(conv64(XB(xbi), WF(n.cidx(g, r, 0)), c1b, B, H, W, st, nullptr, T1(ti), SRES_EPI_RELU));
+      RC(conv64(T1(ti), WF(n.cidx(g, r, 1)), c2b, B, H, W, st, nullptr, T2(ti), fused_pool ? SRES_EPI_POOL : 0,
+                fused_pool ? pool_part : nullptr));
+      if (!fused_pool) RC(sres_ca_pool(T2(ti), pool_sum, B, H, W, st));
+      float* mean = (float*)(ws + n.o_mean) + (size_t)(training ? ti : 0) * B * 64;
+      float* sv = (float*)(ws + n.o_s) + (size_t)(training ? ti : 0) * B * 64;
+      RC(sres_ca_apply_fwd(T2(ti), fused_pool ? pool_part : nullptr, fused_pool ? nullptr : pool_sum, w1, b1, w2, b2,
+                           n.hid, r == 0 ? gin : xf, xf, XB(xbi + 1), mean, sv, B, H, W, st));
+      ++xbi;
+    }
+    const float* pg = P + n.off_gt(g);
+    RC(conv64(XB(xbi), WF(n.cidx_gt(g)), pg + kConvW, B, H, W, st, gout, XB(xbi + 1), 0, nullptr, gin));
+    ++xbi;
+    gin = gout;
+  }
+  void* resb = ws + n.o_resb;
+  RC(conv64(XB(xbi), WF(n.cidx_bt()), P + n.bt_b, B, H, W, st, nullptr, resb, 0, nullptr, hf));
+  const void* cur = resb;
+  for (int i = 0; i < d.n_up; ++i) {
+    const int f = d.up_factor[i];
+    for (int sub = 0; sub < f * f; ++sub)
+      RC(conv64(cur, ws + n.o_wp_up_fwd[i] + (size_t)sub * kConvW * 2, (const float*)(ws + n.o_bias_up[i]) + sub * 64, B,
+                n.lvH[i], n.lvW[i], st, nullptr, ws + n.o_u[i], 0, nullptr, nullptr, nullptr, nullptr, SRES_MAP_SHUFFLE,
+                sub / f, sub % f, f));
+    cur = ws + n.o_u[i];
+  }
+  sres_conv_args a;
+  memset(&a, 0, sizeof(a));
+  a.in_bf16 = cur; a.wpack_bf16 = ws + n.o_wp_tail; a.bias = (const float*)(ws + n.o_bias_tail);
+  a.out_nchw = out; a.c_real = d.cout; a.n_out = 16;
+  a.B = B; a.H = n.lvH[d.n_up]; a.W = n.lvW[d.n_up];
+  RC(sres_conv3x3_igemm(&a, st));
+  return SRES_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward.  Segments: 0 = tail conv, upsampler, body-tail conv; 1..G = residual groups G-1..0;
+// G+1 = head conv.  A caller overlapping the gradient all-reduce runs them one at a time.
+// ---------------------------------------------------------------------------------------------
+static int wgrad64(const void* x, const void* dy, int B, int H, int W, float* dw, float* db, int cout_total, int stride,
+                   int offset, int acc, const Net& n, uint8_t* ws, void* st) {
+  return sres_conv3x3_wgrad(x, dy, B, H, W, dw, db, cout_total, stride, offset, acc, ws + n.o_wg_ws,
+                            sres_conv_wgrad_workspace_bytes(), st);
+}
+
+static int backward(const Net& n, const float* P, const float* x, const float* dout, float* Gr, int accumulate,
+                    uint8_t* ws, int seg_begin, int seg_end, void* st) {
+  const sres_rcan_desc& d = n.d;
+  const int B = d.B, H = d.H, W = d.W, G = d.n_groups, R = d.n_blocks, L = d.n_up;
+  const size_t bf = (size_t)n.lvRows[0] * 128;
+  auto XB = [&](int i) { return ws + n.o_xb + (size_t)i * bf; };
+  auto T1 = [&](int i) { return ws + n.o_t1 + (size_t)i * bf; };
+  auto T2 = [&](int i) { return ws + n.o_t2 + (size_t)i * bf; };
+  auto WD = [&](long long c) { return ws + n.o_wp_dg + (size_t)c * kConvW * 2; };
+  float* ga = (float*)(ws + n.o_ga);
+  float* gb32 = (float*)(ws + n.o_gb32);
+  void* gb16 = ws + n.o_gb16;
+  void* dt2 = ws + n.o_dt2;
+  void* dt1 = ws + n.o_dt1;
+  float* dres32 = (float*)(ws + n.o_dres32);
+  void* dres16 = ws + n.o_dres16;
+  const int xb_last = G * (R + 1);  // bf16 copy of the last group's output = body-tail conv input
+
+  for (int seg = seg_begin; seg < seg_end; ++seg) {
+    if (seg == 0) {
+      const int Hh = n.lvH[L], Wh = n.lvW[L];
+      const void* u_last = L > 0 ? (const void*)(ws + n.o_u[L - 1]) : (const void*)(ws + n.o_resb);
+      RC(sres_small_out_wgrad(dout, u_last, B, d.cout, Hh, Wh, Gr + n.tail_w, Gr + n.tail_b, accumulate, ws + n.o_sw_ws,
+                              sres_small_wgrad_workspace_bytes(), st));
+      if (L == 0) {
+        RC(sres_conv3x3_small_in(dout, P + n.tail_w, nullptr, B, d.cout, Hh, Wh, 1, 0, dres32, dres16, st));
+      } else {
+        RC(sres_conv3x3_small_in(dout, P + n.tail_w, nullptr, B, d.cout, Hh, Wh, 1, d.up_factor[L - 1], nullptr,
+                                 ws + n.o_du16[L - 1], st));
+      }
+      for (int i = L - 1; i >= 0; --i) {
+        const int f = d.up_factor[i], f2 = f * f;
+        const void* cur_in = i > 0 ? (const void*)(ws + n.o_u[i - 1]) : (const void*)(ws + n.o_resb);
+        const size_t sub_bytes = (size_t)n.lvRows[i] * 128;
+        // destination of the input gradient of this stage
+        float* acc32 = i > 0 ? (float*)(ws + n.o_du32[i - 1]) : dres32;
+        void* acc16 = i > 0 ? (void*)(ws + n.o_du16[i - 1]) : dres16;
+        const int map = i > 0 ? SRES_MAP_UNSHUFFLE : SRES_MAP_IDENT;
+        const int sf = i > 0 ? d.up_factor[i - 1] : 2;
+        for (int sub = 0; sub < f2; ++sub) {
+          const void* dy = ws + n.o_du16[i] + sub * sub_bytes;
+          RC(wgrad64(cur_in, dy, B, n.lvH[i], n.lvW[i], Gr + n.up_w[i], Gr + n.up_b[i], f2 * 64, f2, sub, accumulate, n,
+                     ws, st));
+          RC(conv64(dy, ws + n.o_wp_up_dg[i] + (size_t)sub * kConvW * 2, nullptr, B, n.lvH[i], n.lvW[i], st, acc32,
+                    sub == f2 - 1 ? acc16 : nullptr, 0, nullptr, sub > 0 ? acc32 : nullptr, nullptr, nullptr, map, 0, 0,
+                    sf));
+        }
+      }
+      // body-tail conv
+      RC(wgrad64(XB(xb_last), dres16, B, H, W, Gr + n.bt_w, Gr + n.bt_b, 64, 1, 0, accumulate, n, ws, st));
+      RC(conv64(dres16, WD(n.cidx_bt()), nullptr, B, H, W, st, ga, gb16));
+    } else if (seg <= G) {
+      const int g = G - seg;
+      const int xb0 = g * (R + 1);  // XB index of the group's input
+      float* Gg = Gr + n.off_gt(g);
+      RC(wgrad64(XB(xb0 + R), gb16, B, H, W, Gg, Gg + kConvW, 64, 1, 0, accumulate, n, ws, st));
+      RC(conv64(gb16, WD(n.cidx_gt(g)), nullptr, B, H, W, st, gb32, nullptr));
+      for (int r = R - 1; r >= 0; --r) {
+        const int ti = g * R + r;
+        const float* pr = P + n.off_rcab(g, r);
+        float* gr = Gr + n.off_rcab(g, r);
+        const float* w1 = pr + 2 * (kConvW + 64);
+        const float* b1 = w1 + n.hid * 64;
+        const float* w2 = b1 + n.hid;
+        const float* b2 = w2 + 64 * n.hid;
+        const float* mean = (const float*)(ws + n.o_mean) + (size_t)ti * B * 64;
+        float* dsv = (float*)(ws + n.o_ds) + (size_t)ti * B * 64;
+        RC(sres_ca_bwd(gb32, T2(ti), w1, b1, w2, b2, n.hid, mean, (float*)(ws + n.o_ds_part), dt2, dsv, B, H, W, st));
+        RC(wgrad64(T1(ti), dt2, B, H, W, gr + kConvW + 64, gr + 2 * kConvW + 64, 64, 1, 0, accumulate, n, ws, st));
+        RC(conv64(dt2, WD(n.cidx(g, r, 1)), nullptr, B, H, W, st, nullptr, dt1, 0, nullptr, nullptr, nullptr, T1(ti)));
+        RC(wgrad64(XB(xb0 + r), dt1, B, H, W, gr, gr + kConvW, 64, 1, 0, accumulate, n, ws, st));
+        if (r > 0) {
+          RC(conv64(dt1, WD(n.cidx(g, r, 0)), nullptr, B, H, W, st, gb32, nullptr, 0, nullptr, gb32));
+        } else {
+          // grad wrt the group input = body path (gb32 + conv1 dgrad) + group skip (ga)
+          RC(conv64(dt1, WD(n.cidx(g, r, 0)), nullptr, B, H, W, st, ga, gb16, 0, nullptr, gb32, ga));
+        }
+      }
+      const long long first = n.off_rcab(g, 0) + 2 * (kConvW + 64);
+      RC(sres_ca_param_grads(P + first, Gr + first, n.rcab_sz, R, (const float*)(ws + n.o_mean) + (size_t)g * R * B * 64,
+                             (const float*)(ws + n.o_ds) + (size_t)g * R * B * 64, B, n.hid, accumulate, st));
+    } else if (seg == G + 1) {
+      RC(sres_small_in_wgrad(ga, dres32, x, B, d.cin, H, W, Gr + n.head_w, Gr + n.head_b, accumulate, ws + n.o_sw_ws,
+                             sres_small_wgrad_workspace_bytes(), st));
+    }
+  }
+  return SRES_OK;
+}
+
+}  // namespace sres
+
+using namespace sres;
+
+extern "C" int64_t sres_rcan_param_count(const sres_rcan_desc* d) {
+  Net n;
+  if (build_net(&n, d, 0)) return -1;
+  return n.n_params;
+}
+
+extern "C" int sres_rcan_workspace_bytes(const sres_rcan_desc* d, int training, size_t* bytes) {
+  Net n;
+  int rc = build_net(&n, d, training);
+  if (rc) return rc;
+  if (!bytes) return set_error(SRES_ERR_INVALID_ARG, "rcan: null output");
+  *bytes = n.total;
+  return SRES_OK;
+}
+
+extern "C" int sres_rcan_num_segments(const sres_rcan_desc* d) { return d ? d->n_groups + 2 : -1; }
+
+extern "C" int sres_rcan_segment_params(const sres_rcan_desc* d, int seg, int64_t* offset, int64_t* count) {
+  Net n;
+  int rc = build_net(&n, d, 0);
+  if (rc) return rc;
+  if (!offset || !count || seg < 0 || seg > d->n_groups + 1) return set_error(SRES_ERR_INVALID_ARG, "rcan: bad segment");
+  if (seg == 0) { *offset = n.bt_w; *count = n.n_params - n.bt_w; }
+  else if (seg <= d->n_groups) { *offset = n.body0 + (long long)(d->n_groups - seg) * n.group_sz; *count = n.group_sz; }
+  else { *offset = 0; *count = n.body0; }
+  return SRES_OK;
+}
+
+extern "C" int sres_rcan_pack_weights(const sres_rcan_desc* d, const float* params, void* workspace, int training,
+                                      void* stream) {
+  Net n;
+  int rc = build_net(&n, d, training);
+  if (rc) return rc;
+  if (!params || !workspace) return set_error(SRES_ERR_INVALID_ARG, "rcan: null pointer");
+  return pack_all(n, params, (uint8_t*)workspace, (cudaStream_t)stream);
+}
+
+extern "C" int sres_rcan_forward(const sres_rcan_desc* d, const float* params, const float* x_nchw, float* out_nchw,
+                                 void* workspace, int training, void* stream) {
+  Net n;
+  int rc = build_net(&n, d, training);
+  if (rc) return rc;
+  if (!params || !x_nchw || !out_nchw || !workspace) return set_error(SRES_ERR_INVALID_ARG, "rcan: null pointer");
+  return forward(n, params, x_nchw, out_nchw, (uint8_t*)workspace, training, stream);
+}
+
+extern "C" int sres_rcan_backward(const sres_rcan_desc* d, const float* params, const float* x_nchw,
+                                  const float* dout_nchw, float* grads, int accumulate, void* workspace, int seg_begin,
+                                  int seg_end, void* stream) {
+  Net n;
+  int rc = build_net(&n, d, 1);
+  if (rc) return rc;
+  if (!params || !x_nchw || !dout_nchw || !grads || !workspace) return set_error(SRES_ERR_INVALID_ARG, "rcan: null pointer");
+  if (seg_begin < 0 || seg_end > d->n_groups + 2 || seg_begin > seg_end)
+    return set_error(SRES_ERR_INVALID_ARG, "rcan: bad segment range");
+  return backward(n, params, x_nchw, dout_nchw, grads, accumulate, (uint8_t*)workspace, seg_begin, seg_end, stream);
+}

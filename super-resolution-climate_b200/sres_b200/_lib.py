@@ -25,6 +25,7 @@ class ConvArgs(C.Structure):
         ("wpack_bf16", C.c_void_p),
         ("bias", C.c_void_p),
         ("resid_f32", C.c_void_p),
+        ("resid2_f32", C.c_void_p),
         ("mask_bf16", C.c_void_p),
         ("out_f32", C.c_void_p),
         ("out_bf16", C.c_void_p),
@@ -34,6 +35,7 @@ class ConvArgs(C.Structure):
         ("n_out", C.c_int32), ("c_real", C.c_int32),
         ("epi_flags", C.c_uint32),
         ("map_mode", C.c_int32), ("sub_i", C.c_int32), ("sub_j", C.c_int32),
+        ("shuffle_factor", C.c_int32),
         ("debug_flags", C.c_int32),
     ]
 

@@ -1,0 +1,192 @@
+"""Host-side engine over the C ABI: flat parameters, workspaces, forward/backward launches.
+
+PyTorch is plumbing here (device memory, streams, torch.distributed); every FLOP of the hot path is
+executed by libsres_b200.so.  There is no CPU or eager fallback: without a CUDA device or the built
+library every entry point raises.
+"""
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+class RcanDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("cin", C.c_int32), ("cout", C.c_int32), ("nfeatures", C.c_int32),
+        ("n_groups", C.c_int32), ("n_blocks", C.c_int32), ("reduction", C.c_int32),
+        ("n_up", C.c_int32), ("up_factor", C.c_int32 * 4),
+    ]
+
+
+def upsampler_stages(scale: int) -> List[int]:
+    """PixelShuffle factors of the reference Upsampler (sres/model/rcan/blocks.py:62-73)."""
+    if scale >= 1 and scale & (scale - 1) == 0:
+        return [2] * int(round(math.log2(scale)))
+    if scale == 3:
+        return [3]
+    raise NotImplementedError(f"Upsampler: scale {scale}")  # blocks.py:74
+
+
+def param_layout(nchannels_in: int, nchannels_out: int, nfeatures: int, nlayers: int, nblocks: int,
+                 reduction: int, scale: int, kernel_size: int = 3):
+    """Ordered [(state_dict key, shape)] of the reference RCAN (network.py:9-20) == flat-buffer order."""
+    if kernel_size != 3:
+        raise NotImplementedError("sres_b200 RCAN kernels are specialised for kernel_size == 3")
+    out: List[Tuple[str, Tuple[int, ...]]] = []
+
+    def conv(name, cout, cin, k):
+        out.append((name + ".weight", (cout, cin, k, k)))
+        out.append((name + ".bias", (cout,)))
+
+    Fn = nfeatures
+    conv("head.0", Fn, nchannels_in, 3)
+    for g in range(nlayers):
+        for r in range(nblocks):
+            pre = f"body.{g}.body.{r}.body"
+            conv(pre + ".0", Fn, Fn, 3)
+            conv(pre + ".2", Fn, Fn, 3)
+            conv(pre + ".3.conv_du.0", Fn // reduction, Fn, 1)
+            conv(pre + ".3.conv_du.2", Fn, Fn // reduction, 1)
+        conv(f"body.{g}.body.{nblocks}", Fn, Fn, 3)
+    conv(f"body.{nlayers}", Fn, Fn, 3)
+    for i, f in enumerate(upsampler_stages(scale)):
+        conv(f"tail.0.{2 * i}", f * f * Fn, Fn, 3)
+    conv("tail.1", nchannels_out, Fn, 3)
+    return out
+
+
+class RcanEngine:
+    """One RCAN network on one GPU: owns the flat fp32 parameter / gradient buffers and per-shape
+    workspaces, and issues the whole forward / backward kernel sequence with one C call each."""
+
+    def __init__(self, nchannels_in: int, nchannels_out: int, nfeatures: int, nlayers: int, nblocks: int,
+                 reduction: int, scale: int, device: torch.device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise L.SresError(f"sres_b200 RCAN needs a CUDA device (got {device}); there is no CPU fallback")
+        self.lib = L.lib()
+        self.device = device
+        self.cin, self.cout, self.scale = nchannels_in, nchannels_out, scale
+        self.nfeatures, self.nlayers, self.nblocks, self.reduction = nfeatures, nlayers, nblocks, reduction
+        self.stages = upsampler_stages(scale)
+        self.layout = param_layout(nchannels_in, nchannels_out, nfeatures, nlayers, nblocks, reduction, scale)
+        n = sum(int(math.prod(s)) for _, s in self.layout)
+        d = self.desc(1, 8, 8)
+        self.lib.sres_rcan_param_count.restype = C.c_int64
+        n_c = self.lib.sres_rcan_param_count(C.byref(d))
+        if n_c != n:
+            L.check(1 if n_c < 0 else 0, "sres_rcan_param_count")
+            raise L.SresError(f"parameter count mismatch: python {n}, library {n_c}")
+        self.n_params = n
+        self.n_padded = (n + 3) // 4 * 4
+        with torch.cuda.device(device):
+            self.flat = torch.zeros(self.n_padded, device=device, dtype=torch.float32)
+            self.flat_grad = torch.zeros(self.n_padded, device=device, dtype=torch.float32)
+        self._ws: Dict[Tuple[int, int, int, bool], torch.Tensor] = {}
+        self._packed_version: Dict[Tuple[int, int, int, bool], int] = {}
+        self._dirty_token = 0  # bumped by in-place updates torch cannot see (fused Adam)
+        self.launches = 0      # kernels of ours enqueued so far (for bench accounting)
+
+    # -- description / workspace --------------------------------------------------------------
+    def desc(self, B: int, H: int, W: int) -> RcanDesc:
+        d = RcanDesc()
+        d.B, d.H, d.W = B, H, W
+        d.cin, d.cout, d.nfeatures = self.cin, self.cout, self.nfeatures
+        d.n_groups, d.n_blocks, d.reduction = self.nlayers, self.nblocks, self.reduction
+        d.n_up = len(self.stages)
+        for i, f in enumerate(self.stages):
+            d.up_factor[i] = f
+        return d
+
+    def workspace(self, B: int, H: int, W: int, training: bool) -> torch.Tensor:
+        key = (B, H, W, training)
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = C.c_size_t(0)
+            L.check(self.lib.sres_rcan_workspace_bytes(C.byref(self.desc(B, H, W)), int(training), C.byref(nbytes)),
+                    "sres_rcan_workspace_bytes")
+            with torch.cuda.device(self.device):
+                ws = torch.zeros(nbytes.value, dtype=torch.uint8, device=self.device)  # zero-filled: see header
+            self._ws[key] = ws
+        return ws
+
+    def release_workspaces(self):
+        self._ws.clear()
+        self._packed_version.clear()
+
+    def mark_params_changed(self):
+        self._dirty_token += 1
+
+    def _version(self) -> int:
+        return self.flat._version * 1000003 + self._dirty_token
+
+    def _ensure_packed(self, key, ws, stream):
+        v = self._version()
+        if self._packed_version.get(key) != v:
+            B, H, W, training = key
+            L.check(self.lib.sres_rcan_pack_weights(C.byref(self.desc(B, H, W)), L.ptr(self.flat), L.ptr(ws),
+                                                    int(training), stream), "sres_rcan_pack_weights")
+            self._packed_version[key] = v
+
+    # -- kernels launched per call (our claim for bench.py's gpu_launches) ----------------------
+    def launches_forward(self, H: int, W: int) -> int:
+        G, R = self.nlayers, self.nblocks
+        fused = (H + 1) * (W + 1) >= 128
+        per_rcab = 3 if fused else 4
+        return 1 + G * (R * per_rcab + 1) + 1 + sum(f * f for f in self.stages) + 1
+
+    def launches_backward(self) -> int:
+        G, R = self.nlayers, self.nblocks
+        ups = sum(f * f * 3 for f in self.stages)             # wgrad + reduce + dgrad per sub-conv
+        seg0 = 2 + 1 + ups + 2 + 1                              # tail wgrad(2) + tail dgrad + ups + bt wgrad(2) + bt dgrad
+        per_rcab = 2 + 2 + 1 + 2 + 1                            # ca_bwd(2) + wgrad(2) + dgrad + wgrad(2) + dgrad
+        grp = 2 + 1 + R * per_rcab + 1                          # gt wgrad(2) + gt dgrad + rcabs + ca param grads
+        return seg0 + G * grp + 2
+
+    # -- forward / backward ---------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, training: bool) -> torch.Tensor:
+        if x.device != self.device:
+            raise L.SresError(f"input on {x.device}, model on {self.device}")
+        if x.dim() != 4 or x.shape[1] != self.cin:
+            raise ValueError(f"expected (B,{self.cin},H,W) input, got {tuple(x.shape)}")
+        x = x.detach().contiguous().float()
+        B, _, H, W = x.shape
+        key = (B, H, W, bool(training))
+        with torch.cuda.device(self.device):
+            ws = self.workspace(*key)
+            st = L.cur_stream()
+            self._ensure_packed(key, ws, st)
+            sc = self.scale
+            out = torch.empty(B, self.cout, H * sc, W * sc, device=self.device, dtype=torch.float32)
+            L.check(self.lib.sres_rcan_forward(C.byref(self.desc(B, H, W)), L.ptr(self.flat), L.ptr(x), L.ptr(out),
+                                               L.ptr(ws), int(training), st), "sres_rcan_forward")
+        self.launches += self.launches_forward(H, W)
+        return out
+
+    def num_segments(self) -> int:
+        return self.nlayers + 2
+
+    def segment_params(self, seg: int) -> Tuple[int, int]:
+        off, cnt = C.c_int64(0), C.c_int64(0)
+        L.check(self.lib.sres_rcan_segment_params(C.byref(self.desc(1, 8, 8)), seg, C.byref(off), C.byref(cnt)),
+                "sres_rcan_segment_params")
+        return off.value, cnt.value
+
+    def backward(self, x: torch.Tensor, dout: torch.Tensor, accumulate: bool, seg_begin: int = 0,
+                 seg_end: Optional[int] = None):
+        """Gradients of the flat parameter buffer into self.flat_grad for segments [seg_begin, seg_end)."""
+        B, _, H, W = x.shape
+        key = (B, H, W, True)
+        if key not in self._ws:
+            raise L.SresError("backward without a matching training-mode forward")
+        seg_end = self.num_segments() if seg_end is None else seg_end
+        with torch.cuda.device(self.device):
+            L.check(self.lib.sres_rcan_backward(C.byref(self.desc(B, H, W)), L.ptr(self.flat), L.ptr(x), L.ptr(dout),
+                                                L.ptr(self.flat_grad), int(accumulate), L.ptr(self._ws[key]),
+                                                seg_begin, seg_end, L.cur_stream()), "sres_rcan_backward")
+        if seg_begin == 0 and seg_end == self.num_segments():
+            self.launches += self.launches_backward()

@@ -1,0 +1,46 @@
+"""Data parallelism over tile batches: one process per GPU, NCCL all-reduce of the flat gradient
+buffer, issued segment by segment on a side stream so it overlaps the rest of backward.
+
+Not in the reference (single process, single device: sres/base/gpu.py:6-15); SURVEY.md 8e.
+Tiles are independent units (no inter-tile halo, no BatchNorm), weights and optimizer state are
+replicated, the only exchange per step is the gradient sum (+ one scalar for the RMSE loss).
+"""
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous share of `n_items` for `rank` (first ranks take the remainder)."""
+    base, rem = divmod(n_items, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+class SegmentAllReduce:
+    def __init__(self, engine, process_group=None, average: bool = False):
+        if not dist.is_initialized():
+            raise RuntimeError("enable_data_parallel: torch.distributed is not initialised")
+        self.group = process_group
+        self.world = dist.get_world_size(process_group)
+        self.average = average
+        self.comm_stream = torch.cuda.Stream(device=engine.device)
+        self.segments = [engine.segment_params(s) for s in range(engine.num_segments())]
+
+    def backward(self, engine, xin, dout, accumulate: bool):
+        if accumulate:
+            raise RuntimeError("data-parallel backward needs fresh gradients (optimizer.zero_grad() each step)")
+        main = torch.cuda.current_stream(engine.device)
+        for seg, (off, cnt) in enumerate(self.segments):
+            engine.backward(xin, dout, accumulate=False, seg_begin=seg, seg_end=seg + 1)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ev)
+                bucket = engine.flat_grad[off:off + cnt]
+                dist.all_reduce(bucket, group=self.group)
+                if self.average:
+                    bucket.div_(self.world)
+        main.wait_stream(self.comm_stream)
+        engine.launches += engine.launches_backward()
