@@ -41,6 +41,10 @@ struct ConvKParams {
   uint16_t* out_bf16;
   float* pool_part;
   float* out_nchw;
+  // TMA-staged epilogue (identity mapping): per-warp 32-row slabs in shared memory
+  int tma_epi;          // 1: outputs / addends go through smem slabs + TMA, 0: direct global accesses
+  int use_o16, use_msk, use_r32, use_o32;
+  int off_s16, off_msk, off_s32, off_tail;  // byte offsets from the aligned smem base
 };
 
 // 16-value butterfly: after the call lane l (even) holds in v[0] the sum over the 32 lanes of
@@ -86,6 +90,8 @@ __device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
 template <int N_OUT>
 __global__ void __launch_bounds__(256, 1)
 conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                     const __grid_constant__ CUtensorMap tmO16, const __grid_constant__ CUtensorMap tmMsk,
+                     const __grid_constant__ CUtensorMap tmR32, const __grid_constant__ CUtensorMap tmO32,
                      const ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-B aligned carve-up (128B swizzle atoms are 1024 B).
@@ -94,13 +100,17 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint8_t* smem_w = smem;
   uint8_t* smem_a = smem + kWBytes;
   const int stage_bytes = p.stage_rows * 128;
-  uint8_t* tail = smem_a + p.nstage * stage_bytes;
+  uint8_t* tail = smem + p.off_tail;
+  uint8_t* slab16 = smem + p.off_s16;   // [mt][4 warps][32 rows x 128 B]  bf16 output staging
+  uint8_t* slabmk = smem + p.off_msk;   // [mt][4 warps][32 rows x 128 B]  bf16 ReLU-mask tile (TMA loaded)
+  uint8_t* slab32 = smem + p.off_s32;   // [mt][4 warps][2 halves][32 rows x 128 B]  fp32 addend in -> fp32 output
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(tail);  // [kMaxStages]
   uint64_t* bar_empty = bar_full + kMaxStages;              // [kMaxStages]
   uint64_t* bar_w = bar_empty + kMaxStages;                 // [1]
   uint64_t* bar_tfull = bar_w + 1;                          // [2]
   uint64_t* bar_tempty = bar_tfull + 2;                     // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+  uint64_t* bar_in = bar_tempty + 2;                        // [4 warps][2 tiles] epilogue operand loads
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_in + 8);
   float* s_bias = reinterpret_cast<float*>(tmem_holder + 2);  // [N_OUT]
 
   const int warp = threadIdx.x >> 5;
@@ -121,6 +131,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_init(&bar_tfull[i], 1);
       mbar_init(&bar_tempty[i], 4);  // one arrive per epilogue warp
     }
+    for (int i = 0; i < 8; ++i) mbar_init(&bar_in[i], 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -197,11 +208,142 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int s = blockIdx.x; s < p.n_stages; s += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t aph = (it >> 1) & 1;
+      if (p.tma_epi) {
+        // the slabs of the previous stage must have been read out by their TMA stores; then prefetch this
+        // stage's fp32 addend / mask tiles while the tensor core is still working on it
+        if (lane == 0) {
+          bulk_wait_read<0>();
+          if (p.use_msk | p.use_r32) {
+            for (int m = 0; m < p.mt; ++m) {
+              const int tile = s * p.mt + m;
+              if (tile >= p.n_tiles) break;
+              const int row0 = tile * 128 + wq * 32;
+              uint64_t* bi = &bar_in[wq * 2 + m];
+              mbar_expect_tx(bi, (p.use_msk ? 4096u : 0u) + (p.use_r32 ? 8192u : 0u));
+              if (p.use_msk) tma_load_2d(slabmk + (m * 4 + wq) * 4096, &tmMsk, bi, 0, row0);
+              if (p.use_r32) {
+                tma_load_2d(slab32 + (m * 4 + wq) * 8192, &tmR32, bi, 0, row0);
+                tma_load_2d(slab32 + (m * 4 + wq) * 8192 + 4096, &tmR32, bi, 32, row0);
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
       mbar_wait(&bar_tfull[acc], aph, 5);
       tc_fence_after();
       for (int m = 0; m < p.mt; ++m) {
         const int tile = s * p.mt + m;
         if (tile >= p.n_tiles) break;
+        if (p.tma_epi) {
+          // ---------------- TMA-staged epilogue (identity mapping, 64 outputs) ----------------
+          const int row0 = tile * 128 + wq * 32;
+          const int q = row0 + lane;
+          const int b = q / RP;
+          const int rem = q - b * RP;
+          const int y = rem / p.P;
+          const int x = rem - y * p.P;
+          const bool pad = (x == p.W) || (y == p.H) || (q >= p.npos);
+          const int seg = (b != (tile * 128) / RP) ? 1 : 0;
+          const uint32_t trow = tmem_base + (uint32_t(wq * 32) << 16) + uint32_t(acc * acc_cols + m * N_OUT);
+          uint8_t* s16 = slab16 + (m * 4 + wq) * 4096 + lane * 128;
+          const uint8_t* smk = slabmk + (m * 4 + wq) * 4096 + lane * 128;
+          uint8_t* s32 = slab32 + (m * 4 + wq) * 8192 + lane * 128;
+          const int sw = lane & 7;
+          if (p.use_msk | p.use_r32) mbar_wait(&bar_in[wq * 2 + m], it & 1, 6);
+#pragma unroll 1
+          for (int ch = 0; ch < N_OUT / 16; ++ch) {
+            uint32_t raw[16];
+            tmem_ld16(trow + ch * 16, raw);
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) + s_bias[ch * 16 + j];
+            uint8_t* h32 = s32 + (ch >> 1) * 4096;   // half row (32 floats) this chunk lives in
+            const int c32 = (ch & 1) * 4;            // first 16-byte chunk inside that half
+            if (p.use_r32) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 r = *reinterpret_cast<const float4*>(h32 + (((c32 + j) ^ sw) << 4));
+                v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+              }
+            }
+            if (p.resid2 && q < p.npos) {
+              const float4* rp = reinterpret_cast<const float4*>(p.resid2 + (long long)q * 64 + ch * 16);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 r = rp[j];
+                v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+              }
+            }
+            if (p.flags & SRES_EPI_RELU) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (p.use_msk) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint4 mk = *reinterpret_cast<const uint4*>(smk + (((ch * 2 + j) ^ sw) << 4));
+                const uint32_t w4[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (!(bf16_lo(w4[e]) > 0.f)) v[8 * j + 2 * e] = 0.f;
+                  if (!(bf16_hi(w4[e]) > 0.f)) v[8 * j + 2 * e + 1] = 0.f;
+                }
+              }
+            }
+            if (pad) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            }
+            if (p.use_o32) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(h32 + (((c32 + j) ^ sw) << 4)) =
+                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (p.use_o16) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                *reinterpret_cast<uint4*>(s16 + (((ch * 2 + j) ^ sw) << 4)) =
+                    make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            }
+            if (p.flags & SRES_EPI_POOL) {
+              const bool any1 = __any_sync(0xffffffffu, seg == 1);
+              const bool any0 = __any_sync(0xffffffffu, seg == 0);
+              float s0 = 0.f, s1 = 0.f;
+              if (any0) {
+                float t[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) t[j] = seg == 0 ? v[j] : 0.f;
+                s0 = butterfly16(t, lane);
+              }
+              if (any1) {
+                float t[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) t[j] = seg == 1 ? v[j] : 0.f;
+                s1 = butterfly16(t, lane);
+              }
+              if ((lane & 1) == 0) {
+                float* pp = p.pool_part + ((long long)tile * 2 * 4 + wq) * 64 + ch * 16 + (lane >> 1);
+                pp[0] = s0;
+                pp[4 * 64] = s1;
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.use_o16) tma_store_2d(&tmO16, slab16 + (m * 4 + wq) * 4096, 0, row0);
+            if (p.use_o32) {
+              tma_store_2d(&tmO32, slab32 + (m * 4 + wq) * 8192, 0, row0);
+              tma_store_2d(&tmO32, slab32 + (m * 4 + wq) * 8192 + 4096, 32, row0);
+            }
+            bulk_commit();
+          }
+          continue;
+        }
         const int q = tile * 128 + wq * 32 + lane;
         const bool inrange = q < p.npos;
         const int b = q / RP;
@@ -316,6 +458,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[acc]);
     }
+    if (p.tma_epi && lane == 0) bulk_wait_all<0>();
   }
 
   tc_fence_before();
@@ -341,42 +484,67 @@ static int launch_conv(const sres_conv_args* a, cudaStream_t stream) {
   if (npos > 0x7fffff00LL) return set_error(SRES_ERR_UNSUPPORTED, "conv: batch too large for 32-bit rows");
   p.npos = (int)npos;
   p.n_tiles = (p.npos + 127) / 128;
-  p.mt = 2;
-  p.n_stages = (p.n_tiles + p.mt - 1) / p.mt;
-  const int rows = p.mt * 128 + 2 * (p.P + 1);
-  p.stage_rows = (rows + kBoxRows - 1) / kBoxRows * kBoxRows;
-  const int wbytes = 9 * a->n_out * 128;
-  const int smem_max = 232448;  // 227 KB
-  const int fixed = wbytes + 1024 /*align slack*/ + 512 /*barriers, bias*/;
-  int nstage = (smem_max - fixed) / (p.stage_rows * 128);
-  if (nstage > kMaxStages) nstage = kMaxStages;
-  if (nstage < 1) return set_error(SRES_ERR_UNSUPPORTED, "conv: image too wide for the flat halo window");
-  p.nstage = nstage;
   p.n_out = a->n_out; p.c_real = a->c_real;
   p.flags = a->epi_flags; p.map_mode = a->map_mode; p.sub_i = a->sub_i; p.sub_j = a->sub_j; p.sf = sf;
   p.debug_flags = a->debug_flags;
   p.bias = a->bias; p.resid = a->resid_f32; p.resid2 = a->resid2_f32; p.mask = (const uint16_t*)a->mask_bf16;
   p.out_f32 = a->out_f32; p.out_bf16 = (uint16_t*)a->out_bf16; p.pool_part = a->pool_part; p.out_nchw = a->out_nchw;
+  // TMA-staged epilogue whenever rows map to themselves; scattered (PixelShuffle) and planar stores go direct
+  p.tma_epi = (a->map_mode == SRES_MAP_IDENT && a->n_out == 64 && !a->out_nchw && !(a->debug_flags & 2)) ? 1 : 0;
+  if (p.tma_epi) {
+    p.use_o16 = a->out_bf16 != nullptr; p.use_msk = a->mask_bf16 != nullptr;
+    p.use_r32 = a->resid_f32 != nullptr; p.use_o32 = a->out_f32 != nullptr;
+  }
+  const int wbytes = 9 * a->n_out * 128;
+  const int smem_max = 232448;  // 227 KB
+  const int tail_bytes = 1024;
+  const int per_tile_slab = (p.use_o16 ? 16384 : 0) + (p.use_msk ? 16384 : 0) + ((p.use_r32 | p.use_o32) ? 32768 : 0);
+  int chosen = 0;
+  for (int mt = 2; mt >= 1 && !chosen; --mt) {
+    const int rows = mt * 128 + 2 * (p.P + 1);
+    const int stage_rows = (rows + kBoxRows - 1) / kBoxRows * kBoxRows;
+    const int avail = smem_max - 1024 - wbytes - tail_bytes - mt * per_tile_slab;
+    int ns = avail / (stage_rows * 128);
+    if (ns > kMaxStages) ns = kMaxStages;
+    if (ns >= 2 || (mt == 1 && ns >= 1)) {
+      p.mt = mt; p.nstage = ns; p.stage_rows = stage_rows;
+      chosen = 1;
+    }
+  }
+  if (!chosen) return set_error(SRES_ERR_UNSUPPORTED, "conv: image too wide for the flat halo window");
+  p.n_stages = (p.n_tiles + p.mt - 1) / p.mt;
+  int off = wbytes + p.nstage * p.stage_rows * 128;
+  p.off_s16 = off; off += p.use_o16 ? p.mt * 16384 : 0;
+  p.off_msk = off; off += p.use_msk ? p.mt * 16384 : 0;
+  p.off_s32 = off; off += (p.use_r32 | p.use_o32) ? p.mt * 32768 : 0;
+  p.off_tail = off; off += tail_bytes;
+  const size_t smem = (size_t)off + 1024;  // + alignment slack
 
-  CUtensorMap tmA, tmW;
+  CUtensorMap tmA, tmW, tmO16, tmMsk, tmR32, tmO32;
   int rc = make_tmap_rows64(&tmA, a->in_bf16, (uint64_t)p.npos, kBoxRows);
   if (rc) return rc;
   rc = make_tmap_rows64(&tmW, a->wpack_bf16, (uint64_t)(9 * a->n_out), a->n_out);
   if (rc) return rc;
+  tmO16 = tmA; tmMsk = tmA; tmR32 = tmA; tmO32 = tmA;
+  if (p.tma_epi) {
+    if (p.use_o16 && (rc = make_tmap_rows64(&tmO16, a->out_bf16, (uint64_t)p.npos, 32))) return rc;
+    if (p.use_msk && (rc = make_tmap_rows64(&tmMsk, a->mask_bf16, (uint64_t)p.npos, 32))) return rc;
+    if (p.use_r32 && (rc = make_tmap_rows64_f32(&tmR32, a->resid_f32, (uint64_t)p.npos, 32))) return rc;
+    if (p.use_o32 && (rc = make_tmap_rows64_f32(&tmO32, a->out_f32, (uint64_t)p.npos, 32))) return rc;
+  }
 
   int sms = device_sm_count();
   if (sms <= 0) return set_error(SRES_ERR_NO_DEVICE, "conv: no CUDA device");
   const int grid = p.n_stages < sms ? p.n_stages : sms;
-  const size_t smem = (size_t)fixed + (size_t)nstage * p.stage_rows * 128;
   cudaError_t e;
   if (a->n_out == 64) {
-    e = cudaFuncSetAttribute(conv3x3_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(conv3x3_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (e != cudaSuccess) return set_cuda_error(e, "conv: smem attribute");
-    conv3x3_igemm_kernel<64><<<grid, 256, smem, stream>>>(tmA, tmW, p);
+    conv3x3_igemm_kernel<64><<<grid, 256, smem, stream>>>(tmA, tmW, tmO16, tmMsk, tmR32, tmO32, p);
   } else {
-    e = cudaFuncSetAttribute(conv3x3_igemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(conv3x3_igemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (e != cudaSuccess) return set_cuda_error(e, "conv: smem attribute");
-    conv3x3_igemm_kernel<16><<<grid, 256, smem, stream>>>(tmA, tmW, p);
+    conv3x3_igemm_kernel<16><<<grid, 256, smem, stream>>>(tmA, tmW, tmO16, tmMsk, tmR32, tmO32, p);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "conv: launch");

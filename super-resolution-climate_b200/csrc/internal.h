@@ -18,6 +18,10 @@ int device_sm_count();
 // 128B swizzle, zero fill outside [0, nrows).
 int make_tmap_rows64(CUtensorMap* out, const void* base, uint64_t nrows, uint32_t box_rows);
 
+// 2-D TMA descriptor over a row-major [nrows][64] fp32 matrix (256-byte rows), box = 32 floats x box_rows
+// (one 128B-swizzled half row), zero fill outside [0, nrows).
+int make_tmap_rows64_f32(CUtensorMap* out, const void* base, uint64_t nrows, uint32_t box_rows);
+
 #define SRES_CHECK_LAUNCH(where)                                  \
   do {                                                            \
     cudaError_t e__ = cudaGetLastError();                         \

@@ -1,0 +1,310 @@
+"""ModelTrainer, mirror of sres/controller/dual_trainer.py:110-571 for the tile path.
+
+Same public methods and return shapes as the reference controller API:
+  train, evaluate, process_image, apply_network, loss, assemble_images (+ denorm, ttsplit_times).
+Differences are confined to where the work runs: batches stay on the GPU from tile extraction to
+stitching, the model / loss / optimizer are the CUDA kernels, and under torchrun the tile batches of a
+timeslice are sharded across ranks with the gradient all-reduce overlapped with backward.
+"""
+import ctypes as C
+import random
+import time
+from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from sres.base.gpu import set_device
+from sres.base.util.array import array2tensor, downsample, upsample
+from sres.base.util.config import ConfigContext, cfg
+from sres.controller.checkpoints import CheckpointManager
+from sres.controller.config import TSet
+from sres.data.batch import BatchDataset, TileArray
+from sres.data.tiles import TileIterator
+from sres.model.manager import SRModels
+from sres_b200 import _lib as L
+from sres_b200 import nn as _snn
+
+TensorOrTensors = Union[Tensor, Sequence[Tensor]]
+
+
+def ttsplit_times(times: List[int]) -> Dict[TSet, List[int]]:
+    """dual_trainer.py:28-36."""
+    start, result, nt = 0, {}, len(times)
+    for tset, frac in cfg().task.ttsplit.items():
+        end = start + int(frac * nt)
+        result[TSet(tset)] = times[start:end]
+        start = end
+    return result
+
+
+def denorm(t: Tensor, norm_data: Dict[str, Any]) -> Tensor:
+    """dual_trainer.py:67-77, kept on the device (x*std+mean, then optional min/max rescale)."""
+    normed = t.detach()
+    if "mean" in norm_data:
+        normed = (normed * norm_data["std"]) + norm_data["mean"]
+    if "max" in norm_data:
+        normed = (normed * (norm_data["max"] - norm_data["min"])) + norm_data["min"]
+    return normed
+
+
+class ModelTrainer(object):
+
+    def __init__(self, cc: ConfigContext, dataset: Optional[BatchDataset] = None):
+        self.device: torch.device = set_device()
+        self.model_manager: SRModels = SRModels(self.device)
+        if dataset is not None:
+            self.model_manager._dataset = dataset
+        self.context = cc
+        self.min_loss = float("inf")
+        self.eps = 1e-6
+        self.scheduler = None
+        self.model = self.model_manager.get_model()
+        lr, wd = cfg().task.lr, cfg().task.get("weight_decay", 0.0)
+        if cfg().pipeline.get("fused_adam", True):
+            self.optimizer = _snn.FusedAdam(self.model, lr=lr, weight_decay=wd)
+        else:  # the reference's optimizer works too: parameters are ordinary nn.Parameters
+            self.optimizer = torch.optim.Adam(self.model.parameters(), lr=lr, weight_decay=wd)
+        self.checkpoint_manager = CheckpointManager(self.model, self.optimizer)
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        if self.world > 1:
+            self.model.enable_data_parallel()
+        self.input, self.target, self.product, self.interp = {}, {}, {}, {}
+        self.current_losses: Dict[str, float] = {}
+        self.time_index: int = -1
+        self.tile_index: int = -1
+        self.validation_loss: float = float("inf")
+        self.data_timestamps: Dict[TSet, List[int]] = {}
+        self.train_state = None
+
+    # -- plumbing ----------------------------------------------------------------------------------
+    def get_dataset(self) -> BatchDataset:
+        return self.model_manager.get_dataset()
+
+    @property
+    def target_variables(self) -> List[str]:
+        return list(cfg().task.target_variables)
+
+    def load_timeslice(self, ctime, **kwargs) -> Optional[TileArray]:
+        return self.get_dataset().load_timeslice(ctime, **kwargs)
+
+    def get_srbatch(self, ctile: Dict[str, int], ctime, **kwargs) -> Optional[TileArray]:
+        return self.get_dataset().get_batch_array(ctile, ctime, **kwargs)
+
+    def init_data_timestamps(self):
+        if len(self.data_timestamps) == 0:
+            ctimes = self.get_dataset().get_dset_time_indices()
+            random.shuffle(ctimes)
+            self.data_timestamps = ttsplit_times(ctimes)
+
+    # -- the hot path ------------------------------------------------------------------------------
+    def apply_network(self, target_data) -> Tuple[Tensor, TensorOrTensors, Tensor]:
+        """(input, product, target) of one HR batch: bicubic down + model (dual_trainer.py:557-571).
+        Errors propagate (the reference swallows them and returns None, logging.py:13-20)."""
+        data = target_data.data if isinstance(target_data, TileArray) else target_data
+        input_tensor: Tensor = array2tensor(data)
+        dsample = cfg().task.get("data_downsample", 1.0)
+        if dsample > 1.0:
+            input_tensor = downsample(input_tensor, scale_factor=dsample)
+        target_channels: List[str] = self.target_variables
+        output_tensor: Tensor = input_tensor
+        if input_tensor.shape[1] > len(target_channels):
+            tindx = torch.tensor(self.get_dataset().get_channel_idxs(target_channels), device=input_tensor.device)
+            output_tensor = torch.index_select(input_tensor, 1, tindx)
+        input_tensor = downsample(input_tensor)
+        result_tensor: TensorOrTensors = self.model(input_tensor)
+        return input_tensor, result_tensor, output_tensor
+
+    def charbonnier(self, prd: Tensor, tar: Tensor) -> Tensor:
+        return _snn.loss(prd, tar, "charbonnier", self._loss_group())
+
+    def _loss_group(self):
+        return dist.group.WORLD if (self.world > 1 and self.model.training and torch.is_grad_enabled()) else None
+
+    def conform_to_product(self, prd: Tensor, tar: Tensor) -> Tensor:
+        return tar  # the CUDA loss crops the target to the product's (H,W) itself (dual_trainer.py:200-203)
+
+    def single_product_loss(self, prd: Tensor, tar: Tensor) -> Tensor:
+        fn = cfg().model.loss_fn
+        if fn not in ("l2", "charbonnier", "l1"):
+            raise Exception("Unknown single-product loss function {}".format(fn))
+        return _snn.loss(prd, tar, fn, self._loss_group())
+
+    def loss(self, products: TensorOrTensors, target: Tensor) -> Tuple[float, Tensor]:
+        """(python float, differentiable tensor) like dual_trainer.py:221-234 (`.item()` syncs)."""
+        if isinstance(products, torch.Tensor):
+            sloss = self.single_product_loss(products, target)
+            return sloss.item(), sloss
+        raise NotImplementedError("multi-scale product lists are not produced by RCAN")
+
+    def train_step(self, batch) -> Tensor:
+        """One optimizer step on one HR tile batch: zero_grad, forward, loss, backward, step
+        (dual_trainer.py:310-323 without the logging).  Returns the loss as a device scalar."""
+        self.optimizer.zero_grad()
+        _, boutput, btarget = self.apply_network(batch)
+        mloss = self.single_product_loss(boutput, btarget)
+        mloss.backward()
+        self.optimizer.step()
+        return mloss.detach()
+
+    # -- training loop -----------------------------------------------------------------------------
+    def train(self, nepochs: int, refresh_state: bool, **kwargs) -> Dict[str, float]:
+        if nepochs == 0:
+            return {}
+        interp_loss = kwargs.get("interp_loss", False)
+        seed = kwargs.get("seed", 4456)
+        verbose = kwargs.get("verbose", True)
+        torch.manual_seed(seed)
+        torch.cuda.manual_seed(seed)
+        self.scheduler = kwargs.get("scheduler", None)
+        epoch0, itime0, epoch_loss, interp_sloss, tset = 1, 0, 0.0, 0.0, TSet.Train
+        train_start = time.time()
+        if refresh_state:
+            if self.rank == 0:
+                self.checkpoint_manager.clear_checkpoints()
+        else:
+            self.train_state = self.checkpoint_manager.load_checkpoint(TSet.Train, update_model=True) or {}
+            epoch0 = self.train_state.get("epoch", 1)
+            itime0 = self.train_state.get("itime", 0)
+            epoch_loss = self.train_state.get("loss", float("inf"))
+            nepochs += epoch0
+        self.init_data_timestamps()
+        for epoch in range(epoch0, nepochs):
+            self.model.train()
+            nts = len(self.data_timestamps[TSet.Train])
+            for itime in range(itime0, nts):
+                ctime = self.data_timestamps[TSet.Train][itime]
+                timeslice = self.load_timeslice(ctime)
+                tile_iter = TileIterator.get_iterator(ntiles=timeslice.sizes["tiles"], randomize=True)
+                binput = boutput = btarget = None
+                batches = list(iter(tile_iter))
+                # data parallel: every global step consumes `world` consecutive batches of the shuffled order
+                for i0 in range(0, len(batches) - len(batches) % self.world, self.world):
+                    ctile = batches[i0 + self.rank]
+                    batch_data = self.get_srbatch(ctile, ctime)
+                    if batch_data is None:
+                        break
+                    self.optimizer.zero_grad()
+                    binput, boutput, btarget = self.apply_network(batch_data)
+                    [sloss, mloss] = self.loss(boutput, btarget)
+                    tile_iter.register_loss("model", sloss)
+                    if interp_loss:
+                        with torch.no_grad():
+                            [interp_sloss, _] = self.loss(upsample(binput), btarget)
+                        tile_iter.register_loss("interpolated", interp_sloss)
+                    if verbose and self.rank == 0:
+                        pct = (sloss / interp_sloss) * 100 if interp_sloss else float("nan")
+                        print(f" ** <{self.model_manager.model_name}> TRAIN E({epoch:3}/{nepochs}) TIME[{itime:3}:{ctime:4}] "
+                              f"TILES[{ctile['start']:4}:{ctile['end']:4}][F{batch_data.attrs.get('xyflip', 0)}]-> "
+                              f"Loss= {sloss*1000:6.2f} ({interp_sloss*1000:6.2f}): {pct:.2f}%", flush=True)
+                    mloss.backward()
+                    self.optimizer.step()
+                if binput is not None:
+                    self.input[tset] = binput.detach().cpu().numpy()
+                    self.target[tset] = btarget.detach().cpu().numpy()
+                    self.product[tset] = boutput.detach().cpu().numpy()
+                epoch_loss = tile_iter.accumulate_loss("model") if tile_iter.batch_losses("model") else epoch_loss
+                il = tile_iter.accumulate_loss("interpolated") if tile_iter.batch_losses("interpolated") else 0.0
+                if self.rank == 0 and cfg().task.get("checkpoint_every_timeslice", True):
+                    self.checkpoint_manager.save_checkpoint(epoch, itime, TSet.Train, epoch_loss, il)
+            if self.scheduler is not None:
+                self.scheduler.step()
+            itime0 = 0
+        train_time = time.time() - train_start
+        ntotal_params = sum(p.numel() for p in self.model.parameters() if p.requires_grad)
+        if self.rank == 0:
+            print(f" -------> Training model with {ntotal_params} wts took {train_time/60:.2f} min.")
+        self.current_losses = dict(prediction=epoch_loss)
+        return self.current_losses
+
+    # -- inference ---------------------------------------------------------------------------------
+    def process_image(self, tset: TSet, itime: int, **kwargs):
+        """Tile -> batched forward -> stitch for one timeslice (dual_trainer.py:396-447).  Returns
+        (images[var][type] -> 2-D numpy array, losses[var] -> dict(model, interpolated))."""
+        seed = kwargs.get("seed", 333)
+        cfg().task["xyflip"] = False
+        torch.manual_seed(seed)
+        if kwargs.get("update_model", False):
+            self.train_state = self.checkpoint_manager.load_checkpoint(TSet.Validation, **kwargs)
+            if self.train_state is None:
+                print("Error loading checkpoint file, skipping evaluation.")
+                return {}, {}
+        self.time_index = itime
+        self.init_data_timestamps()
+        ctime = kwargs.get("ctime", None)
+        if ctime is None:
+            ctime = self.data_timestamps[TSet.Train][itime]
+        timeslice = self.load_timeslice(ctime)
+        vnames, cvar = self.target_variables, kwargs.get("var", None)
+        output_vars = [cvar] if cvar is not None else vnames
+        batch_model_losses, batch_interp_losses, batches = [], [], []
+        tile_iter = TileIterator.get_iterator(ntiles=timeslice.sizes["tiles"])
+        with torch.no_grad():
+            for ctile in iter(tile_iter):
+                batch_data = self.get_srbatch(ctile, ctime, shuffle=False)
+                if batch_data is None:
+                    break
+                binput, boutput, btarget = self.apply_network(batch_data)
+                binterp = upsample(binput)
+                batch_model_losses.append(self.loss(boutput, btarget)[0])
+                batch_interp_losses.append(self.loss(binterp, btarget)[0])
+                a = batch_data.attrs
+                batches.append(dict(input=denorm(binput, a), target=denorm(btarget, a), interpolated=denorm(binterp, a),
+                                    model=denorm(boutput, a)))
+        images, losses = {}, {}
+        for ivar, vname in enumerate(output_vars):
+            images[vname] = self.assemble_images(batches, ivar, timeslice.coords["tiles"], timeslice.attrs["grid_shape"])
+            losses[vname] = dict(model=float(np.array(batch_model_losses).mean()),
+                                 interpolated=float(np.array(batch_interp_losses).mean()))
+        return images, losses
+
+    def assemble_images(self, batches: List[Dict[str, Tensor]], ivar: int, tile_ids, grid_shape: Dict[str, int]) -> Dict[str, np.ndarray]:
+        """Place tile `tid` at grid cell (tid // gx, tid % gx), NaN elsewhere (dual_trainer.py:449-480), on
+        the GPU.  dtype rule of the reference's np.block: float64 iff at least one cell stayed empty."""
+        lib = L.lib()
+        gy, gx = int(grid_shape["y"]), int(grid_shape["x"])
+        tile_ids = np.asarray(tile_ids)
+        out: Dict[str, np.ndarray] = {}
+        for image_type in batches[0].keys():
+            tiles = torch.cat([torch.as_tensor(b[image_type], device=self.device).float() for b in batches], dim=0).contiguous()
+            n, Cc, t, _ = tiles.shape
+            cell = np.full(gy * gx, -1, dtype=np.int32)
+            for i in range(n):           # later tiles overwrite earlier ones, like the reference's loop
+                cell[int(tile_ids[i])] = i
+            cell_d = torch.from_numpy(cell).to(self.device)
+            img = torch.empty(gy * t, gx * t, dtype=torch.float32, device=self.device)
+            L.check(lib.sres_tiles_stitch(L.ptr(tiles), Cc, ivar, t, gy, gx, L.ptr(cell_d), None, None, L.ptr(img),
+                                          L.cur_stream()), "sres_tiles_stitch")
+            arr = img.cpu().numpy()
+            out[image_type] = arr.astype(np.float64) if (cell < 0).any() else arr
+        return out
+
+    def evaluate(self, tset: TSet, **kwargs):
+        """Batched forward over the tiles of a validation/test timeslice (dual_trainer.py:482-543).
+        Returns (dict(input,target,model,interpolated) -> numpy (N,C,·,·), dict(model, interpolated))."""
+        assert tset in [TSet.Validation, TSet.Test], f"Invalid tset in training evaluation: {tset.name}"
+        self.time_index = kwargs.get("time_index", self.time_index)
+        self.init_data_timestamps()
+        ml, il, res = [], [], dict(input=[], target=[], model=[], interpolated=[])
+        with torch.no_grad():
+            for itime, ctime in enumerate(self.data_timestamps.get(tset, [])):
+                if (self.time_index < 0) or (itime == self.time_index):
+                    timeslice = self.load_timeslice(ctime)
+                    for ctile in iter(TileIterator.get_iterator(ntiles=timeslice.sizes["tiles"])):
+                        batch_data = self.get_srbatch(ctile, ctime)
+                        if batch_data is None:
+                            break
+                        binput, boutput, btarget = self.apply_network(batch_data)
+                        binterp = upsample(binput)
+                        ml.append(self.loss(boutput, btarget)[0])
+                        il.append(self.loss(binterp, btarget)[0])
+                        for k, v in zip(res.keys(), (binput, btarget, boutput, binterp)):
+                            res[k].append(v.detach())
+                    if self.time_index >= 0:
+                        break
+        results = {k: (torch.cat(v).cpu().numpy() if v else None) for k, v in res.items()}
+        losses = dict(model=float(np.mean(ml)) if ml else float("nan"), interpolated=float(np.mean(il)) if il else float("nan"))
+        return results, losses

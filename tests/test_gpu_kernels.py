@@ -1,0 +1,287 @@
+"""GPU parity tests, kernel by kernel, through the C ABI, against the CPU oracle's arithmetic
+(plain fp32 PyTorch ops on the CPU -- the reference's own math).  Tolerances: the tensor-core kernels
+take bf16 operands with fp32 accumulation, so they are compared with fp32 math on the SAME
+bf16-rounded operands at 2e-3 relative (accumulation order only); fp32 kernels at 1e-5."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import rcan_oracle as O
+from gpu_util import bf16_round, conv_args, from_ptl, pack, pads_are_zero, ptr, rel_l2, run_conv, to_ptl
+
+pytestmark = pytest.mark.gpu
+GEOMS = [(1, 48, 48), (3, 20, 24), (2, 5, 7), (2, 96, 96), (5, 12, 12)]
+
+
+@pytest.fixture(scope="module")
+def env():
+    from sres_b200 import _lib as L
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    torch.manual_seed(1234)
+    return L, L.lib(), torch.device("cuda:0")
+
+
+def _rand(dev, *shape, scale=1.0):
+    return bf16_round(torch.randn(*shape) * scale), None
+
+
+@pytest.mark.parametrize("B,H,W", GEOMS)
+def test_conv_forward_bias_relu_pool(env, B, H, W):
+    L, lib, dev = env
+    x = bf16_round(torch.randn(B, 64, H, W))
+    w = bf16_round(torch.randn(64, 64, 3, 3) * 0.05)
+    b = torch.randn(64)
+    ref = F.relu(F.conv2d(x, w, b, padding=1))
+    xp = to_ptl(x.to(dev), torch.bfloat16)
+    rows = xp.shape[0]
+    out32 = torch.full((rows, 64), float("nan"), device=dev)
+    out16 = torch.zeros(rows, 64, device=dev, dtype=torch.bfloat16)
+    nt = lib.sres_conv_mtiles(B, H, W)
+    pool = torch.full((nt, 2, 4, 64), float("nan"), device=dev)
+    fused = (H + 1) * (W + 1) >= 128
+    a = conv_args(in_bf16=xp, wpack_bf16=pack(lib, w.to(dev), 0), bias=b.to(dev), out_f32=out32, out_bf16=out16,
+                  B=B, H=H, W=W, n_out=64, epi_flags=L.EPI_RELU | (L.EPI_POOL if fused else 0))
+    if fused:
+        a.pool_part = pool.data_ptr()
+    run_conv(lib, a)
+    assert pads_are_zero(out32, B, H, W) and pads_are_zero(out16, B, H, W)
+    assert rel_l2(from_ptl(out32, B, H, W).cpu(), ref) < 2e-3
+    assert rel_l2(from_ptl(out16, B, H, W).cpu(), ref) < 6e-3          # + one bf16 rounding of the output
+    if fused:
+        RP = (H + 1) * (W + 1)
+        sums = torch.zeros(B, 64)
+        pc = pool.cpu()
+        assert torch.isfinite(pc).all()
+        for t in range(nt):
+            b0 = (t * 128) // RP
+            for seg in range(2):
+                if b0 + seg < B:
+                    sums[b0 + seg] += pc[t, seg].sum(0)
+        assert rel_l2(sums, ref.sum((2, 3))) < 1e-4
+
+
+@pytest.mark.parametrize("B,H,W", GEOMS[:3])
+def test_conv_dgrad_mask_residuals(env, B, H, W):
+    """Input gradient = conv with transposed/flipped weights; ReLU-backward mask; two fp32 addends."""
+    L, lib, dev = env
+    dy = bf16_round(torch.randn(B, 64, H, W))
+    w = bf16_round(torch.randn(64, 64, 3, 3) * 0.05)
+    t1 = bf16_round(torch.randn(B, 64, H, W)).clamp_min(0)
+    r1, r2 = torch.randn(B, 64, H, W), torch.randn(B, 64, H, W)
+    dx = F.conv_transpose2d(dy, w, None, padding=1)
+    ref_mask = dx * (t1 > 0)
+    ref_res = dx + r1 + r2
+    dyp = to_ptl(dy.to(dev), torch.bfloat16)
+    wp = pack(lib, w.to(dev), 1)
+    out16 = torch.zeros(dyp.shape[0], 64, device=dev, dtype=torch.bfloat16)
+    run_conv(lib, conv_args(in_bf16=dyp, wpack_bf16=wp, mask_bf16=to_ptl(t1.to(dev), torch.bfloat16), out_bf16=out16,
+                            B=B, H=H, W=W, n_out=64))
+    assert rel_l2(from_ptl(out16, B, H, W).cpu(), ref_mask) < 6e-3 and pads_are_zero(out16, B, H, W)
+    acc = to_ptl(r1.to(dev), torch.float32)
+    run_conv(lib, conv_args(in_bf16=dyp, wpack_bf16=wp, resid_f32=acc, resid2_f32=to_ptl(r2.to(dev), torch.float32), out_f32=acc,
+                            B=B, H=H, W=W, n_out=64))
+    assert rel_l2(from_ptl(acc, B, H, W).cpu(), ref_res) < 2e-3 and pads_are_zero(acc, B, H, W)
+
+
+@pytest.mark.parametrize("f", [2, 3])
+def test_upsampler_conv_pixelshuffle_and_back(env, f):
+    """conv 64->f*f*64 + PixelShuffle(f) as f*f sub-convs with shuffled stores (blocks.py:62-73), and the
+    inverse addressing used by the backward pass."""
+    L, lib, dev = env
+    B, H, W = 2, 12, 10
+    x = bf16_round(torch.randn(B, 64, H, W))
+    w = bf16_round(torch.randn(f * f * 64, 64, 3, 3) * 0.05)
+    b = torch.randn(f * f * 64)
+    ref = F.pixel_shuffle(F.conv2d(x, w, b, padding=1), f)
+    xp = to_ptl(x.to(dev), torch.bfloat16)
+    lib.sres_ptl_rows.restype = C.c_int64
+    out16 = torch.full((lib.sres_ptl_rows(B, f * H, f * W), 64), float("nan"), device=dev, dtype=torch.bfloat16)
+    for sub in range(f * f):
+        bsub = b[sub::f * f].contiguous().to(dev)
+        run_conv(lib, conv_args(in_bf16=xp, wpack_bf16=pack(lib, w.to(dev), 0, 64, f * f, sub), bias=bsub, out_bf16=out16,
+                                B=B, H=H, W=W, n_out=64, map_mode=L.MAP_SHUFFLE, sub_i=sub // f, sub_j=sub % f, shuffle_factor=f))
+    assert torch.isfinite(out16.float()).all() and pads_are_zero(out16, B, f * H, f * W)
+    assert rel_l2(from_ptl(out16, B, f * H, f * W).cpu(), ref) < 6e-3
+    # unshuffle store: identity-weight conv of the hi-res tensor lands in f*f low-res sub-grids
+    hi = bf16_round(torch.randn(B, 64, f * H, f * W))
+    wid = torch.zeros(64, 64, 3, 3)
+    wid[torch.arange(64), torch.arange(64), 1, 1] = 1.0
+    rows_lo = lib.sres_ptl_rows(B, H, W)
+    sub16 = torch.zeros(f * f * rows_lo, 64, device=dev, dtype=torch.bfloat16)
+    run_conv(lib, conv_args(in_bf16=to_ptl(hi.to(dev), torch.bfloat16), wpack_bf16=pack(lib, wid.to(dev), 0), out_bf16=sub16,
+                            B=B, H=f * H, W=f * W, n_out=64, map_mode=L.MAP_UNSHUFFLE, shuffle_factor=f))
+    un = F.pixel_unshuffle(hi, f).reshape(B, 64, f * f, H, W)
+    for sub in range(f * f):
+        got = from_ptl(sub16[sub * rows_lo:(sub + 1) * rows_lo], B, H, W).cpu()
+        assert torch.equal(got, un[:, :, sub])
+
+
+@pytest.mark.parametrize("B,H,W", GEOMS[:4])
+def test_conv_wgrad(env, B, H, W):
+    L, lib, dev = env
+    lib.sres_conv_wgrad_workspace_bytes.restype = C.c_size_t
+    x = bf16_round(torch.randn(B, 64, H, W))
+    dy = bf16_round(torch.randn(B, 64, H, W))
+    ref = torch.nn.grad.conv2d_weight(x, (64, 64, 3, 3), dy, padding=1)
+    wsb = lib.sres_conv_wgrad_workspace_bytes()
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    dw = torch.full((64, 64, 3, 3), float("nan"), device=dev)
+    db = torch.full((64,), float("nan"), device=dev)
+    xp, dyp = to_ptl(x.to(dev), torch.bfloat16), to_ptl(dy.to(dev), torch.bfloat16)
+
+    def run(acc):
+        L.check(lib.sres_conv3x3_wgrad(ptr(xp), ptr(dyp), B, H, W, ptr(dw), ptr(db), 64, 1, 0, acc, ptr(ws),
+                                       C.c_size_t(wsb), L.cur_stream()), "wgrad")
+        torch.cuda.synchronize()
+    run(0)
+    assert rel_l2(dw.cpu(), ref) < 2e-3 and rel_l2(db.cpu(), dy.sum((0, 2, 3))) < 1e-4
+    first = dw.clone()
+    run(0)
+    assert torch.equal(dw, first), "wgrad must be deterministic run to run"
+    run(1)
+    assert rel_l2(dw.cpu(), 2 * ref) < 2e-3
+
+
+def test_head_and_tail_convs(env):
+    """Cin->64 head conv, 64->Cout tail conv (tensor cores, N padded to 16), their gradients."""
+    L, lib, dev = env
+    lib.sres_small_wgrad_workspace_bytes.restype = C.c_size_t
+    wsb = lib.sres_small_wgrad_workspace_bytes()
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    for Cs, B, H, W in [(2, 3, 20, 24), (1, 2, 9, 9), (4, 1, 16, 12)]:
+        x = torch.randn(B, Cs, H, W)
+        w, b = torch.randn(64, Cs, 3, 3) * 0.2, torch.randn(64)
+        ref = F.conv2d(x, w, b, padding=1)
+        rows = B * (H + 1) * (W + 1)
+        o32 = torch.full((rows, 64), float("nan"), device=dev)
+        o16 = torch.zeros(rows, 64, device=dev, dtype=torch.bfloat16)
+        xd = x.to(dev)
+        L.check(lib.sres_conv3x3_small_in(ptr(xd), ptr(w.to(dev)), ptr(b.to(dev)), B, Cs, H, W, 0, 0, ptr(o32), ptr(o16),
+                                          L.cur_stream()), "head")
+        torch.cuda.synchronize()
+        assert rel_l2(from_ptl(o32, B, H, W).cpu(), ref) < 1e-5 and pads_are_zero(o32, B, H, W) and pads_are_zero(o16, B, H, W)
+        # head wgrad with two gradient addends
+        g1, g2 = torch.randn(B, 64, H, W), torch.randn(B, 64, H, W)
+        dw = torch.empty(64, Cs, 3, 3, device=dev)
+        db = torch.empty(64, device=dev)
+        L.check(lib.sres_small_in_wgrad(ptr(to_ptl(g1.to(dev), torch.float32)), ptr(to_ptl(g2.to(dev), torch.float32)), ptr(xd),
+                                        B, Cs, H, W, ptr(dw), ptr(db), 0, ptr(ws), C.c_size_t(wsb), L.cur_stream()), "head wgrad")
+        torch.cuda.synchronize()
+        assert rel_l2(dw.cpu(), torch.nn.grad.conv2d_weight(x, (64, Cs, 3, 3), g1 + g2, padding=1)) < 1e-4
+        assert rel_l2(db.cpu(), (g1 + g2).sum((0, 2, 3))) < 1e-4
+        # tail conv forward 64 -> Cs on the tensor cores
+        u = bf16_round(torch.randn(B, 64, H, W))
+        wt, bt = bf16_round(torch.randn(Cs, 64, 3, 3) * 0.05), torch.randn(Cs)
+        up = to_ptl(u.to(dev), torch.bfloat16)
+        bias16 = torch.zeros(16, device=dev)
+        bias16[:Cs] = bt.to(dev)
+        out = torch.full((B, Cs, H, W), float("nan"), device=dev)
+        run_conv(lib, conv_args(in_bf16=up, wpack_bf16=pack(lib, wt.to(dev), 0, 16), bias=bias16, out_nchw=out, c_real=Cs,
+                                B=B, H=H, W=W, n_out=16))
+        assert rel_l2(out.cpu(), F.conv2d(u, wt, bt, padding=1)) < 2e-3
+        # tail dgrad (planar gradient -> 64-feature PTL) and tail wgrad
+        dout = torch.randn(B, Cs, H, W)
+        d16 = torch.zeros(rows, 64, device=dev, dtype=torch.bfloat16)
+        d32 = torch.zeros(rows, 64, device=dev)
+        L.check(lib.sres_conv3x3_small_in(ptr(dout.to(dev)), ptr(wt.to(dev)), None, B, Cs, H, W, 1, 0, ptr(d32), ptr(d16),
+                                          L.cur_stream()), "tail dgrad")
+        torch.cuda.synchronize()
+        assert rel_l2(from_ptl(d32, B, H, W).cpu(), F.conv_transpose2d(dout, wt, None, padding=1)) < 1e-5
+        dwt = torch.empty(Cs, 64, 3, 3, device=dev)
+        dbt = torch.empty(Cs, device=dev)
+        L.check(lib.sres_small_out_wgrad(ptr(dout.to(dev)), ptr(up), B, Cs, H, W, ptr(dwt), ptr(dbt), 0, ptr(ws),
+                                         C.c_size_t(wsb), L.cur_stream()), "tail wgrad")
+        torch.cuda.synchronize()
+        assert rel_l2(dwt.cpu(), torch.nn.grad.conv2d_weight(u, (Cs, 64, 3, 3), dout, padding=1)) < 1e-4
+        assert rel_l2(dbt.cpu(), dout.sum((0, 2, 3))) < 1e-4
+
+
+@pytest.mark.parametrize("B,H,W,red", [(3, 20, 24, 2), (2, 48, 48, 16), (4, 7, 9, 4)])
+def test_channel_attention_forward_backward(env, B, H, W, red):
+    """CALayer + RCAB residual against autograd of the oracle's ca_layer (network.py:44-47, 61-64)."""
+    L, lib, dev = env
+    hid = 64 // red
+    t2 = bf16_round(torch.randn(B, 64, H, W)).requires_grad_(True)
+    x = torch.randn(B, 64, H, W)
+    sd = {"ca.conv_du.0.weight": (torch.randn(hid, 64, 1, 1) * 0.3).requires_grad_(True), "ca.conv_du.0.bias": torch.randn(hid).requires_grad_(True),
+          "ca.conv_du.2.weight": (torch.randn(64, hid, 1, 1) * 0.3).requires_grad_(True), "ca.conv_du.2.bias": torch.randn(64).requires_grad_(True)}
+    out_ref = O.ca_layer(t2, sd, "ca") + x
+    g = torch.randn(B, 64, H, W)
+    out_ref.backward(g)
+    w1, b1, w2, b2 = [sd[k].detach().reshape(sd[k].shape[0], -1).contiguous().to(dev) for k in sd]
+    t2p = to_ptl(t2.detach().to(dev), torch.bfloat16)
+    rows = t2p.shape[0]
+    pool_sum = torch.empty(B, 64, device=dev)
+    L.check(lib.sres_ca_pool(ptr(t2p), ptr(pool_sum), B, H, W, L.cur_stream()), "ca_pool")
+    xo = torch.full((rows, 64), float("nan"), device=dev)
+    xb = torch.zeros(rows, 64, device=dev, dtype=torch.bfloat16)
+    mean, sv = torch.empty(B, 64, device=dev), torch.empty(B, 64, device=dev)
+    L.check(lib.sres_ca_apply_fwd(ptr(t2p), None, ptr(pool_sum), ptr(w1), ptr(b1), ptr(w2), ptr(b2), hid,
+                                  ptr(to_ptl(x.to(dev), torch.float32)), ptr(xo), ptr(xb), ptr(mean), ptr(sv), B, H, W,
+                                  L.cur_stream()), "ca_apply_fwd")
+    torch.cuda.synchronize()
+    assert rel_l2(from_ptl(xo, B, H, W).cpu(), out_ref.detach()) < 1e-5 and pads_are_zero(xo, B, H, W)
+    assert rel_l2(mean.cpu(), t2.detach().mean((2, 3))) < 1e-5
+    bpi = lib.sres_ca_blocks_per_image(B, H, W)
+    ds_part = torch.empty(B * bpi * 64, device=dev)
+    dt2 = torch.full((rows, 64), 7.0, device=dev, dtype=torch.bfloat16)
+    ds = torch.empty(B, 64, device=dev)
+    L.check(lib.sres_ca_bwd(ptr(to_ptl(g.to(dev), torch.float32)), ptr(t2p), ptr(w1), ptr(b1), ptr(w2), ptr(b2), hid,
+                            ptr(mean), ptr(ds_part), ptr(dt2), ptr(ds), B, H, W, L.cur_stream()), "ca_bwd")
+    torch.cuda.synchronize()
+    assert rel_l2(from_ptl(dt2, B, H, W).cpu(), t2.grad) < 6e-3 and pads_are_zero(dt2, B, H, W)
+    # parameter gradients: one "layer" laid out as [w1,b1,w2,b2]
+    flat = torch.cat([w1.flatten(), b1.flatten(), w2.flatten(), b2.flatten()])
+    gflat = torch.full_like(flat, float("nan"))
+    L.check(lib.sres_ca_param_grads(ptr(flat), ptr(gflat), C.c_int64(flat.numel()), 1, ptr(mean), ptr(ds), B, hid, 0,
+                                    L.cur_stream()), "ca_param_grads")
+    torch.cuda.synchronize()
+    ref_flat = torch.cat([sd[k].grad.flatten() for k in sd])
+    assert rel_l2(gflat.cpu(), ref_flat) < 1e-4
+
+
+def test_bicubic_matches_interpolate(env):
+    L, lib, dev = env
+    from sres_b200 import nn as snn
+    for shape, s in [((3, 2, 192, 192), 4), ((2, 1, 20, 28), 2), ((1, 4, 64, 64), 8), ((2, 2, 27, 27), 3)]:
+        x = torch.randn(*shape)
+        down = snn.bicubic_resize(x.to(dev), 1.0 / s)
+        ref = O.downsample(x, s)
+        assert down.shape == ref.shape and (down.cpu() - ref).abs().max() < 2e-6
+        up = snn.bicubic_resize(down, s)
+        assert (up.cpu() - O.upsample(ref, s)).abs().max() < 5e-6
+
+
+@pytest.mark.parametrize("kind", ["l2", "charbonnier", "l1"])
+def test_losses_and_gradients(env, kind):
+    L, lib, dev = env
+    from sres_b200 import nn as snn
+    prd = torch.randn(3, 2, 40, 40, requires_grad=True)
+    tar = torch.randn(3, 2, 44, 42)                                  # larger target: conform_to_product crops it
+    ref = O.single_product_loss(prd, tar, kind)
+    (ref * 1.7).backward()
+    p = prd.detach().to(dev).requires_grad_(True)
+    got = snn.loss(p, tar.to(dev), kind)
+    (got * 1.7).backward()
+    assert abs(got.item() - ref.item()) < 1e-6 * max(1.0, abs(ref.item()))
+    assert rel_l2(p.grad.cpu(), prd.grad) < 1e-5
+
+
+def test_fused_adam_matches_torch_adam(env):
+    L, lib, dev = env
+    n = 4 * 1001
+    p0, steps = torch.randn(n), 5
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=3e-3, weight_decay=0.01)
+    p, m, v = p0.to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    for t in range(1, steps + 1):
+        g = torch.randn(n) * (0.1 if t % 2 else 1e-6)
+        ref.grad = g.clone()
+        opt.step()
+        L.check(lib.sres_adam_step_flat(ptr(p), ptr(g.to(dev)), ptr(m), ptr(v), C.c_int64(n), C.c_int64(t), C.c_double(3e-3),
+                                        C.c_double(0.9), C.c_double(0.999), C.c_double(1e-8), C.c_double(0.01), L.cur_stream()), "adam")
+    torch.cuda.synchronize()
+    assert (p.cpu() - ref.detach()).abs().max() < 1e-5

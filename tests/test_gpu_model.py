@@ -1,0 +1,281 @@
+"""GPU parity of the whole path: model forward/backward/Adam vs the oracle and the reference's golden
+vectors, tile extraction / normalisation / flip / stitching bit-exact vs the oracle, and the mirror of
+the reference controller API end to end.  Floating-point tolerance (BASELINE.json north_star): global
+rel-L2 <= 1e-2 on outputs and on the full gradient (bf16 operands, fp32 accumulation)."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import rcan_oracle as O
+import tiles_oracle as T
+from gpu_util import rel_l2
+from synth import MODEL_CASES, TILE_CASES, sha, synth_hr, synth_region
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    torch.set_num_threads(os.cpu_count() or 1)
+    return torch.device("cuda:0")
+
+
+def _build(cfg, C, dev_):
+    from sres_b200 import nn as snn
+    return snn.RCAN(nchannels_in=C, nchannels_out=C, nfeatures=64, nlayers=cfg["nlayers"], nblocks=cfg["nblocks"],
+                    cbottleneck=cfg["cbottleneck"], scale=O.scale_of(cfg), device=dev_)
+
+
+@pytest.mark.parametrize("name", list(MODEL_CASES))
+def test_train_step_matches_oracle_and_golden(name, dev, golden_dir):
+    from sres_b200 import nn as snn
+    over, B, S, C, loss_name, smooth, full_out = MODEL_CASES[name]
+    gold = np.load(os.path.join(golden_dir, f"rcan_{name}.npz"))
+    cfg = O.model_cfg(**over)
+    scale = O.scale_of(cfg)
+    sd = O.make_state_dict(cfg, C, C)
+    hr = synth_hr(B, C, S * scale, smooth=smooth)
+    loss_o, prd_o, grads_o = O.loss_and_grads(hr, sd, cfg, loss_name)
+    model = _build(cfg, C, dev)
+    assert [k for k, _ in model.named_parameters()] == list(sd.keys()) == [str(n) for n in gold["grad_names"]]
+    model.load_state_dict(sd)
+    opt = snn.FusedAdam(model, lr=1e-4)
+    hr_d = hr.to(dev)
+    lr_d = snn.bicubic_resize(hr_d, 1.0 / scale)
+    assert (lr_d.cpu()[: gold["lr_input"].shape[0]] - torch.from_numpy(gold["lr_input"])).abs().max() < 2e-6
+    prd = model(lr_d.requires_grad_(True))
+    loss = snn.loss(prd, hr_d, loss_name)
+    loss.backward()
+    # vs oracle
+    assert rel_l2(prd.detach().cpu(), prd_o) < TOL
+    assert abs(loss.item() - loss_o) < TOL * abs(loss_o)
+    num = sum((p.grad.cpu() - grads_o[k]).double().pow(2).sum().item() for k, p in model.named_parameters())
+    den = sum(g.double().pow(2).sum().item() for g in grads_o.values())
+    assert (num / den) ** 0.5 < TOL
+    # vs the reference's own numbers (golden fixture)
+    out = prd.detach().cpu().numpy() if full_out else prd.detach().cpu().numpy()[:, :, ::8, ::8]
+    assert np.linalg.norm(out - gold["output"]) / np.linalg.norm(gold["output"]) < TOL
+    assert abs(loss.item() - float(gold["loss"])) < TOL * float(gold["loss"])
+    gn = np.array([p.grad.double().norm().item() for _, p in model.named_parameters()])
+    big = gold["grad_norms"] > 0.05 * gold["grad_norms"].max()
+    np.testing.assert_allclose(gn[big], gold["grad_norms"][big], rtol=3e-2)
+    for key in ("head.0.weight", "tail.1.weight", "tail.1.bias"):
+        g = dict(model.named_parameters())[key].grad.cpu().numpy()
+        assert np.linalg.norm(g - gold["grad::" + key]) / np.linalg.norm(gold["grad::" + key]) < 2 * TOL
+    # exact identity: d loss / d tail bias = sum of the output gradient
+    # one fused Adam step from the oracle's gradients must reproduce the oracle's Adam
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            p.grad.copy_(grads_o[k])
+    opt.step()
+    adam = O.AdamState(sd, lr=1e-4)
+    with torch.no_grad():
+        adam.step(sd, grads_o)
+    for k, p in model.named_parameters():
+        assert (p.detach().cpu() - sd[k]).abs().max() < 1e-6, k
+    # inference mode (no grad) runs the same kernels without saved activations
+    model.load_state_dict(O.make_state_dict(cfg, C, C))
+    with torch.no_grad():
+        prd2 = model(lr_d.detach())
+    assert rel_l2(prd2.cpu(), prd_o) < TOL
+
+
+def test_gradient_accumulation_and_stock_adam(dev):
+    """Two backward passes without zero_grad accumulate (autograd semantics); torch.optim.Adam works on the
+    parameter views and its in-place update is picked up by the next forward (weights are re-packed)."""
+    from sres_b200 import nn as snn
+    cfg = O.model_cfg(nlayers=1, nblocks=1)
+    model = _build(cfg, 2, dev)
+    model.load_state_dict(O.make_state_dict(cfg, 2, 2))
+    x = torch.randn(2, 2, 12, 12, device=dev)
+    tgt = torch.randn(2, 2, 48, 48, device=dev)
+    snn.loss(model(x.requires_grad_(True)), tgt, "l2").backward()
+    g1 = model.engine.flat_grad.clone()
+    snn.loss(model(x), tgt, "l2").backward()
+    assert rel_l2(model.engine.flat_grad, 2 * g1) < 1e-5
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    out0 = model(x).detach().clone()
+    opt.step()
+    out1 = model(x).detach()
+    assert (out1 - out0).abs().max() > 1e-4
+    opt.zero_grad()
+    assert all(p.grad is None for p in model.parameters())
+    snn.loss(model(x), tgt, "l2").backward()
+    assert all(p.grad is not None for p in model.parameters())
+
+
+def test_loss_decreases_when_training(dev):
+    from sres_b200 import nn as snn
+    cfg = O.model_cfg(nlayers=2, nblocks=2)
+    torch.manual_seed(0)
+    model = _build(cfg, 2, dev)
+    opt = snn.FusedAdam(model, lr=2e-4)
+    hr = synth_hr(8, 2, 96, smooth=True).to(dev)
+    lr_in = snn.bicubic_resize(hr, 0.25)
+    losses = []
+    for _ in range(30):
+        opt.zero_grad()
+        loss = snn.loss(model(lr_in.requires_grad_(True)), hr, "l2")
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert np.isfinite(losses).all() and losses[-1] < 0.7 * losses[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# tiles: bit-exact
+# ------------------------------------------------------------------------------------------------
+def _tile_inputs(C, Y, X, seed, same_mask):
+    var = synth_region(C, Y, X, seed)
+    if C > 1 and same_mask:
+        m = np.isnan(var[0])
+        for v in var[1:]:
+            v[np.isnan(v)] = 0.5
+            v[m] = np.nan
+    return var
+
+
+def _dataset(C, tile, scale, order="reference", batch_size=7, region=None):
+    from sres.base.util.config import ConfigContext
+    from sres.data.batch import BatchDataset
+    ConfigContext.deactivate()
+    ConfigContext.set_defaults(task="SSS_SST-tiles-48" if C == 2 else "SST-tiles-48", dataset="synthetic_1200", platform="local")
+    dfs = {2: [2], 4: [2, 2], 8: [2, 2, 2]}[scale]
+    cc = ConfigContext.activate_global("sres", model="rcan-10-20-64", **{
+        "task.batch_size": batch_size, "task.tile_size": dict(x=tile, y=tile), "task.tile_order": order,
+        "model.downscale_factors": dfs, "model.nlayers": 1, "model.nblocks": 1})
+    return cc, BatchDataset(region_source=(lambda t: region) if region is not None else None)
+
+
+@pytest.mark.parametrize("name", [n for n in TILE_CASES if TILE_CASES[n][6]])
+def test_tiles_extract_norm_flip_stitch_bit_exact(name, dev, golden_dir):
+    from sres.base.util.config import ConfigContext
+    C, Y, X, tile, scale, seed, same_mask = TILE_CASES[name]
+    gold = np.load(os.path.join(golden_dir, f"tiles_{name}.npz"))
+    var = _tile_inputs(C, Y, X, seed, same_mask)
+    region = np.concatenate(var, 0)
+    cc, ds = _dataset(C, tile, scale, region=region)
+    try:
+        ts = ds.load_timeslice(0)
+        tiles_o, ids_o, gs_o = T.get_tiles(var, dict(x=tile, y=tile), scale)
+        got = ts.values
+        assert got.shape == tiles_o.shape and sha(got) == sha(tiles_o) == str(gold["tiles_sha"])      # bit-exact
+        np.testing.assert_array_equal(ts.coords["tiles"], gold["tile_ids"])
+        assert ts.attrs["grid_shape"] == gs_o
+        # lnorm: floating point (mean/std reductions) -> tolerance; flips: exact permutations of it
+        nb = ds.select_batch((7, 14))
+        nb_o, st_o = T.lnorm(T.select_batch(tiles_o, 7, 14))
+        np.testing.assert_allclose(nb.values, nb_o, rtol=0, atol=2e-5)
+        np.testing.assert_allclose(nb.attrs["mean"].cpu().numpy(), st_o["mean"], rtol=1e-6)
+        np.testing.assert_allclose(nb.attrs["std"].cpu().numpy(), st_o["std"], rtol=1e-5)
+        base = nb.values
+        for fi in range(8):
+            fb = ds.norm(ts.data[7:14], (7, 14), fi)
+            np.testing.assert_array_equal(fb.values, T.xyflip(base, fi))
+        assert ds.select_batch((ts.shape[0], ts.shape[0] + 7)) is None
+        assert list(ds.select_batch((ts.shape[0] - 3, ts.shape[0] + 4)).shape) == list(gold["last_batch_shape"])
+        # stitching of raw tiles is bit-exact against the oracle AND against the reference's image hash
+        from sres.controller.dual_trainer import ModelTrainer
+        tr = object.__new__(ModelTrainer)
+        tr.device = dev
+        batches_o, batches_g = [], []
+        for b in T.tile_batches(tiles_o.shape[0], 7):
+            raw = T.select_batch(tiles_o, b["start"], b["end"])
+            batches_o.append(dict(target=raw, input=np.ascontiguousarray(raw[:, :, ::scale, ::scale])))
+            batches_g.append({k: torch.from_numpy(v).to(dev) for k, v in batches_o[-1].items()})
+        for ivar in range(C):
+            imgs_o = T.assemble_images(batches_o, ivar, ids_o, gs_o)
+            imgs_g = tr.assemble_images(batches_g, ivar, ts.coords["tiles"], ts.attrs["grid_shape"])
+            for k in imgs_o:
+                assert imgs_g[k].dtype == imgs_o[k].dtype and sha(imgs_g[k]) == sha(imgs_o[k])
+                assert int(np.isnan(imgs_g[k]).sum()) == int(gold[f"image_{ivar}_{k}_nan"])
+                assert list(imgs_g[k].shape) == list(gold[f"image_{ivar}_{k}_shape"])
+    finally:
+        ConfigContext.deactivate()
+
+
+def test_tiles_reference_quirk_and_corrected_order(dev):
+    from sres.base.util.config import ConfigContext
+    C, Y, X, tile, scale, seed, same_mask = TILE_CASES["c2_diffmask"]
+    var = _tile_inputs(C, Y, X, seed, same_mask)
+    region = np.concatenate(var, 0)
+    cc, ds = _dataset(C, tile, scale, order="reference", region=region)
+    try:
+        with pytest.raises(ValueError, match="cannot reshape"):
+            ds.load_timeslice(0)
+    finally:
+        ConfigContext.deactivate()
+    cc, ds = _dataset(C, tile, scale, order="corrected", region=region)
+    try:
+        ts = ds.load_timeslice(0)
+        tiles_o, ids_o, _ = T.get_tiles(var, dict(x=tile, y=tile), scale, mode="corrected")
+        assert sha(ts.values) == sha(tiles_o)
+        np.testing.assert_array_equal(ts.coords["tiles"], ids_o)
+    finally:
+        ConfigContext.deactivate()
+
+
+def test_full_size_region_roundtrip(dev):
+    """Config 4 size: (1, 3000, 17280) region, 15 x 90 grid: stitch(extract(region)) reproduces the region
+    bit for bit on surviving tiles and is NaN elsewhere (size-independent property, no oracle needed)."""
+    from sres.base.util.config import ConfigContext
+    from sres.controller.dual_trainer import ModelTrainer
+    from sres.data.batch import synthetic_region
+    region = synthetic_region(1, 3000, 17280, seed=5)
+    cc, ds = _dataset(1, 48, 4, batch_size=64, region=region)
+    try:
+        ts = ds.load_timeslice(0)
+        gs = ts.attrs["grid_shape"]
+        assert gs == dict(x=90, y=15) and 0 < ts.shape[0] < 1350
+        tr = object.__new__(ModelTrainer)
+        tr.device = dev
+        img = tr.assemble_images([dict(target=ts.data)], 0, ts.coords["tiles"], gs)["target"]
+        crop = region[0, :15 * 192, :90 * 192]
+        keep = np.zeros(1350, dtype=bool)
+        keep[ts.coords["tiles"]] = True
+        mask = np.repeat(np.repeat(keep.reshape(15, 90), 192, 0), 192, 1)
+        assert np.array_equal(img[mask].astype(np.float32), crop[mask]) and np.isnan(img[~mask]).all()
+        assert np.isfinite(crop[mask]).all()
+    finally:
+        ConfigContext.deactivate()
+
+
+# ------------------------------------------------------------------------------------------------
+# the mirror of the reference controller API, end to end
+# ------------------------------------------------------------------------------------------------
+def test_controller_api_train_and_infer(dev, tmp_path):
+    from sres.base.util.config import ConfigContext, cfg
+    from sres.controller.config import ResultStructure, TSet
+    from sres.controller.workflow import WorkflowController
+    ConfigContext.deactivate()
+    random.seed(3)
+    wc = WorkflowController("sres", dict(task="SSS_SST-tiles-48", dataset="synthetic_1200", platform="local"), seed=1)
+    wc.initialize("sres", "rcan-10-20-64", **{
+        "model.nlayers": 2, "model.nblocks": 2, "task.batch_size": 8, "task.lr": 2e-4, "task.tile_size": dict(x=12, y=12),
+        "task.tile_order": "corrected", "dataset.region": dict(ys=480, xs=480), "dataset.ntimes": 4,
+        "task.ttsplit": dict(train=0.75, valid=0.25, test=0.0), "platform.results": str(tmp_path)})
+    try:
+        tr = wc.trainer
+        assert type(tr.model).__module__ == "sres.model.rcan.network" and cfg().task.training_version.startswith("sres-rcan")
+        first = tr.train(2, True, seed=4456, interp_loss=True, verbose=False)
+        again = tr.train(1, False, seed=4456, interp_loss=True, verbose=False)   # resumes from the checkpoint
+        assert np.isfinite(first["prediction"]) and np.isfinite(again["prediction"])
+        assert os.path.exists(tr.checkpoint_manager.checkpoint_path(TSet.Train))
+        ck = torch.load(tr.checkpoint_manager.checkpoint_path(TSet.Train), map_location="cpu", weights_only=False)
+        assert set(ck) == {"epoch", "itime", "model_state_dict", "optimizer_state_dict", "loss"}
+        assert list(ck["model_state_dict"].keys()) == list(O.param_shapes(O.model_cfg(nlayers=2, nblocks=2), 2, 2).keys())
+        images, losses = wc.inference(0, ResultStructure.Image)
+        assert set(images) == {"SSS", "SST"}
+        for v in images:
+            assert set(images[v]) == {"input", "target", "interpolated", "model"}
+            assert images[v]["target"].shape == (480 // 48 * 48, 480 // 48 * 48) and images[v]["input"].shape == (120, 120)
+            assert np.isfinite(losses[v]["model"]) and losses[v]["interpolated"] > 0
+        res, l2 = tr.evaluate(TSet.Validation, time_index=0)
+        assert res["model"].shape[1:] == (2, 48, 48) and np.isfinite(l2["model"])
+    finally:
+        ConfigContext.deactivate()

@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--debug-flags", type=int, default=0)
     ap.add_argument("--mode", default="fwd", choices=["fwd", "dgrad", "relu_pool", "shuffle", "resid"])
     ap.add_argument("--iters", type=int, default=0)
+    ap.add_argument("--bf16-only", action="store_true")
     a = ap.parse_args()
     torch.manual_seed(0)
     torch.backends.cudnn.allow_tf32 = False
@@ -72,6 +73,8 @@ def main():
     elif a.mode == "fwd":
         args.out_f32 = out_f32.data_ptr()
         args.out_bf16 = out_bf16.data_ptr()
+        if a.bf16_only:
+            args.out_f32 = None
         ref = F.conv2d(x, w, bias, padding=1)
     elif a.mode == "dgrad":
         args.out_f32 = out_f32.data_ptr()
@@ -117,8 +120,9 @@ def main():
     if a.nout == 16:
         got = out_nchw
     else:
-        got = from_ptl(out_f32, B, H, W)
-        full = out_f32.reshape(B, H + 1, W + 1, 64)
+        src = out_bf16 if (a.mode == "fwd" and a.bf16_only) else out_f32
+        got = from_ptl(src, B, H, W)
+        full = src.reshape(B, H + 1, W + 1, 64).float()
         print("pad row max", full[:, H].abs().max().item(), "pad col max", full[:, :, W].abs().max().item())
     err = (got - ref).abs().max().item()
     rel = ((got - ref).norm() / ref.norm()).item()
