@@ -155,10 +155,12 @@ SRES_API int sres_ca_apply_fwd(const void* t2_bf16, const float* pool_part, cons
 SRES_API int sres_ca_bwd(const float* grad_f32, const void* t2_bf16, const float* w1, const float* b1,
                          const float* w2, const float* b2, int hidden, const float* save_mean, float* ds_part,
                          void* dt2_bf16, float* save_ds, int B, int H, int W, void* stream);
-/* parameter gradients of `nlayers` CALayers whose parameters sit layer_stride floats apart       */
+/* parameter gradients of `nlayers` CALayers whose parameters sit layer_stride floats apart;
+ * scratch: sres_ca_param_grads_scratch_bytes(nlayers, B) bytes of device memory                   */
+SRES_API size_t sres_ca_param_grads_scratch_bytes(int nlayers, int B);
 SRES_API int sres_ca_param_grads(const float* params_first, float* grads_first, int64_t layer_stride, int nlayers,
                                  const float* save_mean, const float* save_ds, int B, int hidden, int accumulate,
-                                 void* stream);
+                                 void* scratch, size_t scratch_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Bicubic resize = F.interpolate(mode="bicubic", align_corners=False)                         */

@@ -207,68 +207,77 @@ struct CaParamBatch {
   const float* mean;     // [njobs][B][64] saved by forward
   const float* ds;       // [njobs][B][64] saved by backward
 };
-struct CaParamJob {
-  const float *w1, *b1, *w2, *b2;
-  float *dw1, *db1, *dw2, *db2;
-  const float *mean, *ds;
-};
 
+// pass 1: one block per (layer, image): dz = ds*s*(1-s), h = relu(W1 m + b1), dh = relu'(.) * W2^T dz
 __global__ void __launch_bounds__(kCaThreads)
-ca_param_grad_kernel(const CaParamBatch batch, int B, int hid, int accumulate) {
-  __shared__ float sm_m[64], sm_h[kCaMaxHidden], sm_z[64], sm_s[64], sm_dz[64], sm_dh[kCaMaxHidden];
-  CaParamJob job;
-  {
-    const long long o = (long long)blockIdx.x * batch.layer_stride;
-    job.w1 = batch.params + o;           job.dw1 = batch.grads + o;
-    job.b1 = job.w1 + hid * 64;          job.db1 = job.dw1 + hid * 64;
-    job.w2 = job.b1 + hid;               job.dw2 = job.db1 + hid;
-    job.b2 = job.w2 + 64 * hid;          job.db2 = job.dw2 + 64 * hid;
-    job.mean = batch.mean + (size_t)blockIdx.x * B * 64;
-    job.ds = batch.ds + (size_t)blockIdx.x * B * 64;
+ca_param_prep_kernel(const CaParamBatch batch, int B, int hid, float* __restrict__ scratch) {
+  __shared__ float sm_m[64], sm_h[kCaMaxHidden], sm_z[64], sm_s[64], sm_dz[64];
+  const int layer = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const long long o = (long long)layer * batch.layer_stride;
+  const float* w1 = batch.params + o;
+  const float* b1 = w1 + hid * 64;
+  const float* w2 = b1 + hid;
+  const float* b2 = w2 + 64 * hid;
+  if (tid < 64) sm_m[tid] = batch.mean[((size_t)layer * B + b) * 64 + tid];
+  __syncthreads();
+  ca_mlp(w1, b1, w2, b2, hid, sm_m, sm_h, sm_z, sm_s);
+  float* out = scratch + ((size_t)layer * B + b) * (64 + 2 * kCaMaxHidden);  // [dz 64][h 64][dh 64]
+  if (tid < 64) {
+    const float s = sm_s[tid];
+    const float dz = batch.ds[((size_t)layer * B + b) * 64 + tid] * s * (1.f - s);
+    sm_dz[tid] = dz;
+    out[tid] = dz;
   }
-  const int tid = threadIdx.x;
-  const int n12 = hid * 64;  // elements of each weight matrix
-  float a1[16], a2[16];       // thread owns elements tid, tid+256, ... of dw1 and dw2 (n12 <= 4096)
+  __syncthreads();
+  if (tid < hid) {
+    float a = 0.f;
+    for (int c = 0; c < 64; ++c) a = fmaf(w2[c * hid + tid], sm_dz[c], a);
+    out[64 + tid] = sm_h[tid];
+    out[64 + kCaMaxHidden + tid] = sm_h[tid] > 0.f ? a : 0.f;
+  }
+}
+
+// pass 2: one block per layer: outer-product sums over the batch in a fixed order (deterministic)
+__global__ void __launch_bounds__(kCaThreads)
+ca_param_sum_kernel(const CaParamBatch batch, int B, int hid, const float* __restrict__ scratch, int accumulate) {
+  const int layer = blockIdx.x, tid = threadIdx.x;
+  const long long o = (long long)layer * batch.layer_stride;
+  float* dw1 = batch.grads + o;
+  float* db1 = dw1 + hid * 64;
+  float* dw2 = db1 + hid;
+  float* db2 = dw2 + 64 * hid;
+  const int n12 = hid * 64;
+  float a1[16], a2[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) a1[i] = a2[i] = 0.f;
   float ab1 = 0.f, ab2 = 0.f;
   for (int b = 0; b < B; ++b) {
-    __syncthreads();
-    if (tid < 64) sm_m[tid] = job.mean[b * 64 + tid];
-    __syncthreads();
-    ca_mlp(job.w1, job.b1, job.w2, job.b2, hid, sm_m, sm_h, sm_z, sm_s);
-    if (tid < 64) {
-      const float s = sm_s[tid];
-      sm_dz[tid] = job.ds[b * 64 + tid] * s * (1.f - s);
-    }
-    __syncthreads();
-    if (tid < hid) {
-      float a = 0.f;
-      for (int c = 0; c < 64; ++c) a = fmaf(job.w2[c * hid + tid], sm_dz[c], a);
-      sm_dh[tid] = sm_h[tid] > 0.f ? a : 0.f;
-    }
-    __syncthreads();
+    const float* sc = scratch + ((size_t)layer * B + b) * (64 + 2 * kCaMaxHidden);
+    const float* dz = sc;
+    const float* h = sc + 64;
+    const float* dh = sc + 64 + kCaMaxHidden;
+    const float* m = batch.mean + ((size_t)layer * B + b) * 64;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int e = tid + i * kCaThreads;
       if (e < n12) {
-        a1[i] = fmaf(sm_dh[e / 64], sm_m[e % 64], a1[i]);   // dw1[j][c] = dh[j] * m[c]
-        a2[i] = fmaf(sm_dz[e / hid], sm_h[e % hid], a2[i]); // dw2[c][j] = dz[c] * h[j]
+        a1[i] = fmaf(__ldg(dh + e / 64), __ldg(m + e % 64), a1[i]);    // dw1[j][c] = dh[j] * m[c]
+        a2[i] = fmaf(__ldg(dz + e / hid), __ldg(h + e % hid), a2[i]);  // dw2[c][j] = dz[c] * h[j]
       }
     }
-    if (tid < hid) ab1 += sm_dh[tid];
-    if (tid < 64) ab2 += sm_dz[tid];
+    if (tid < hid) ab1 += __ldg(dh + tid);
+    if (tid < 64) ab2 += __ldg(dz + tid);
   }
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int e = tid + i * kCaThreads;
     if (e < n12) {
-      job.dw1[e] = accumulate ? job.dw1[e] + a1[i] : a1[i];
-      job.dw2[e] = accumulate ? job.dw2[e] + a2[i] : a2[i];
+      dw1[e] = accumulate ? dw1[e] + a1[i] : a1[i];
+      dw2[e] = accumulate ? dw2[e] + a2[i] : a2[i];
     }
   }
-  if (tid < hid) job.db1[tid] = accumulate ? job.db1[tid] + ab1 : ab1;
-  if (tid < 64) job.db2[tid] = accumulate ? job.db2[tid] + ab2 : ab2;
+  if (tid < hid) db1[tid] = accumulate ? db1[tid] + ab1 : ab1;
+  if (tid < 64) db2[tid] = accumulate ? db2[tid] + ab2 : ab2;
 }
 
 static int ca_geom(CaGeom* g, int B, int H, int W, int hid) {
@@ -339,14 +348,22 @@ extern "C" int sres_ca_bwd(const float* grad_f32, const void* t2_bf16, const flo
   return SRES_OK;
 }
 
+extern "C" size_t sres_ca_param_grads_scratch_bytes(int nlayers, int B) {
+  return (size_t)(nlayers > 0 ? nlayers : 0) * (B > 0 ? B : 0) * (64 + 2 * kCaMaxHidden) * sizeof(float);
+}
+
 extern "C" int sres_ca_param_grads(const float* params_first, float* grads_first, int64_t layer_stride, int nlayers,
                                    const float* save_mean, const float* save_ds, int B, int hidden, int accumulate,
-                                   void* stream) {
-  if (!params_first || !grads_first || !save_mean || !save_ds || nlayers <= 0)
+                                   void* scratch, size_t scratch_bytes, void* stream) {
+  if (!params_first || !grads_first || !save_mean || !save_ds || !scratch || nlayers <= 0 || B <= 0)
     return set_error(SRES_ERR_INVALID_ARG, "ca_param_grads: bad argument");
   if (hidden < 1 || hidden > kCaMaxHidden) return set_error(SRES_ERR_UNSUPPORTED, "ca: hidden width must be 1..64");
+  if (scratch_bytes < sres_ca_param_grads_scratch_bytes(nlayers, B))
+    return set_error(SRES_ERR_INVALID_ARG, "ca_param_grads: scratch too small");
   CaParamBatch batch{params_first, grads_first, (long long)layer_stride, save_mean, save_ds};
-  ca_param_grad_kernel<<<nlayers, kCaThreads, 0, (cudaStream_t)stream>>>(batch, B, hidden, accumulate);
-  SRES_CHECK_LAUNCH("ca_param_grads: launch");
+  ca_param_prep_kernel<<<dim3(nlayers, B), kCaThreads, 0, (cudaStream_t)stream>>>(batch, B, hidden, (float*)scratch);
+  SRES_CHECK_LAUNCH("ca_param_grads: prep launch");
+  ca_param_sum_kernel<<<nlayers, kCaThreads, 0, (cudaStream_t)stream>>>(batch, B, hidden, (const float*)scratch, accumulate);
+  SRES_CHECK_LAUNCH("ca_param_grads: sum launch");
   return SRES_OK;
 }

@@ -92,6 +92,22 @@ int make_tmap_rows64_f32(CUtensorMap* out, const void* base, uint64_t nrows, uin
   return SRES_OK;
 }
 
+int make_tmap_rows64_half(CUtensorMap* out, const void* base, uint64_t nrows, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(SRES_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(base) & 127) != 0)
+    return set_error(SRES_ERR_INVALID_ARG, "TMA operand must be 128-byte aligned");
+  cuuint64_t dims[2] = {64, nrows};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(SRES_ERR_CUDA, "cuTensorMapEncodeTiled (bf16 half rows) failed");
+  return SRES_OK;
+}
+
 }  // namespace sres
 
 extern "C" int sres_abi_version(void) { return 1; }

@@ -42,10 +42,10 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_done + 1);
   float* s_db = reinterpret_cast<float*>(tmem_holder + 2);  // [4][64]
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmDY);
     for (int i = 0; i < kWgMaxStages; ++i) {
@@ -62,50 +62,61 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
+    const bool leader = elect_one();
+    {
       int it = 0;
       for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x, ++it) {
         const int slot = it % p.nstage;
         const uint32_t ph = (it / p.nstage) & 1;
         mbar_wait(&bar_empty[slot], ph ^ 1, 11);
-        mbar_expect_tx(&bar_full[slot], stage_bytes);
         uint8_t* dst = smem + slot * stage_bytes;
         const int q0 = c * 128;
-        tma_load_2d(dst, &tmDY, &bar_full[slot], 0, q0);
-        tma_load_2d(dst + 64 * 128, &tmDY, &bar_full[slot], 0, q0 + 64);
-        uint8_t* xdst = dst + 128 * 128;
-        const int x0 = q0 - (p.P + 1);
-        for (int r = 0; r < p.xrows; r += 64) tma_load_2d(xdst + r * 128, &tmX, &bar_full[slot], 0, x0 + r);
+        if (leader) {
+          mbar_expect_tx(&bar_full[slot], stage_bytes);
+          tma_load_2d(dst, &tmDY, &bar_full[slot], 0, q0);
+          tma_load_2d(dst + 64 * 128, &tmDY, &bar_full[slot], 0, q0 + 64);
+          uint8_t* xdst = dst + 128 * 128;
+          const int x0 = q0 - (p.P + 1);
+          for (int r = 0; r < p.xrows; r += 64) tma_load_2d(xdst + r * 128, &tmX, &bar_full[slot], 0, x0 + r);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    const bool leader = elect_one();
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+      constexpr uint32_t dhi = sdesc_hi_sw128(1024);
       const uint32_t s_addr = smem_u32(smem);
+      uint32_t xoff[kWgAcc];
+#pragma unroll
+      for (int a = 0; a < kWgAcc; ++a) xoff[a] = uint32_t(p.off_a[a]) * 8 + ((uint32_t(p.lbo[a]) >> 4) << 16);
       int it = 0;
       for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x, ++it) {
         const int slot = it % p.nstage;
         const uint32_t ph = (it / p.nstage) & 1;
         mbar_wait(&bar_full[slot], ph, 12);
         tc_fence_after();
-        const uint32_t dy_addr = s_addr + slot * stage_bytes;
-        const uint32_t x_addr = dy_addr + 128 * 128;
+        const uint32_t dy_lo = sdesc_lo(s_addr + slot * stage_bytes, 1024);
+        const uint32_t x_lo = sdesc_lo(s_addr + slot * stage_bytes + 128 * 128, 0);
 #pragma unroll
         for (int a = 0; a < kWgAcc; ++a) {
-          const uint32_t xa = x_addr + uint32_t(p.off_a[a]) * 128;
+          const uint32_t xa = x_lo + xoff[a];
+          if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint64_t da = make_sdesc_sw128(xa + kk * 2048, uint32_t(p.lbo[a]), 1024, 0);
-            const uint64_t db = make_sdesc_sw128(dy_addr + kk * 2048, 1024, 1024, 0);
-            umma_bf16(tmem_base + a * 64, da, db, idesc, (it | kk) ? 1u : 0u);
+            for (int kk = 0; kk < 8; ++kk) {
+              if (kk == 0) umma_bf16_lohi_p(tmem_base + a * 64, xa, dhi, dy_lo, dhi, idesc, it ? 1u : 0u);
+              else umma_bf16_lohi<true>(tmem_base + a * 64, xa + kk * 128, dhi, dy_lo + kk * 128, dhi, idesc);
+            }
           }
         }
-        umma_commit(&bar_empty[slot]);
+        __syncwarp();
+        if (leader) umma_commit(&bar_empty[slot]);
       }
-      umma_commit(bar_done);
+      if (leader) umma_commit(bar_done);
     }
   } else if (warp >= 4) {
     // bias gradient: column sums of the dY tile, read straight from the swizzled smem rows.

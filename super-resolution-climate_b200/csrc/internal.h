@@ -22,6 +22,10 @@ int make_tmap_rows64(CUtensorMap* out, const void* base, uint64_t nrows, uint32_
 // (one 128B-swizzled half row), zero fill outside [0, nrows).
 int make_tmap_rows64_f32(CUtensorMap* out, const void* base, uint64_t nrows, uint32_t box_rows);
 
+// 2-D TMA descriptor over a [nrows][64] bf16 matrix with a HALF-row box (32 channels = 64 bytes) x box_rows,
+// 64B swizzle: the per-warp epilogue slabs of the conv kernel.
+int make_tmap_rows64_half(CUtensorMap* out, const void* base, uint64_t nrows, uint32_t box_rows);
+
 #define SRES_CHECK_LAUNCH(where)                                  \
   do {                                                            \
     cudaError_t e__ = cudaGetLastError();                         \

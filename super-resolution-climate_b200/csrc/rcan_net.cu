@@ -31,7 +31,7 @@ struct Net {
   size_t o_wp_fwd, o_wp_dg, o_wp_up_fwd[4], o_wp_up_dg[4], o_wp_tail, o_bias_up[4], o_bias_tail;
   size_t o_xb, o_t1, o_t2, o_mean, o_s, o_ds, o_resb, o_u[4];
   size_t o_hf, o_gf[2], o_xf, o_pool_part, o_pool_sum;
-  size_t o_ga, o_gb32, o_gb16, o_dt2, o_dt1, o_ds_part, o_wg_ws, o_sw_ws, o_du16[4], o_du32[4], o_dres32, o_dres16;
+  size_t o_ga, o_gb32, o_gb16, o_dt2, o_dt1, o_ds_part, o_wg_ws, o_sw_ws, o_ca_scr, o_du16[4], o_du32[4], o_dres32, o_dres16;
   size_t total;
   int n_xb, n_t;  // saved-buffer counts (1 in inference mode)
   long long cidx(int g, int r, int which) const { return (long long)g * (2 * d.n_blocks + 1) + 2 * r + which; }
@@ -123,6 +123,7 @@ static int build_net(Net* n, const sres_rcan_desc* d, int training) {
     n->o_ds_part = take((size_t)d->B * (bpi > 0 ? bpi : 1) * 64 * 4);
     n->o_wg_ws = take(sres_conv_wgrad_workspace_bytes());
     n->o_sw_ws = take(sres_small_wgrad_workspace_bytes());
+    n->o_ca_scr = take(sres_ca_param_grads_scratch_bytes(R, d->B));
     for (int i = 0; i < d->n_up; ++i) {
       // gradient w.r.t. U[i] (level i+1), stored as f*f sub-grids of level-i rows (PixelUnshuffle layout)
       const int f2 = d->up_factor[i] * d->up_factor[i];
@@ -374,7 +375,8 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
       }
       const long long first = n.off_rcab(g, 0) + 2 * (kConvW + 64);
       RC(sres_ca_param_grads(P + first, Gr + first, n.rcab_sz, R, (const float*)(ws + n.o_mean) + (size_t)g * R * B * 64,
-                             (const float*)(ws + n.o_ds) + (size_t)g * R * B * 64, B, n.hid, accumulate, st));
+                             (const float*)(ws + n.o_ds) + (size_t)g * R * B * 64, B, n.hid, accumulate, ws + n.o_ca_scr,
+                             sres_ca_param_grads_scratch_bytes(R, B), st));
     } else if (seg == G + 1) {
       RC(sres_small_in_wgrad(ga, dres32, x, B, d.cin, H, W, Gr + n.head_w, Gr + n.head_b, accumulate, ws + n.o_sw_ws,
                              sres_small_wgrad_workspace_bytes(), st));

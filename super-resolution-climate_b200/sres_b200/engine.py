@@ -144,7 +144,7 @@ class RcanEngine:
         ups = sum(f * f * 3 for f in self.stages)             # wgrad + reduce + dgrad per sub-conv
         seg0 = 2 + 1 + ups + 2 + 1                              # tail wgrad(2) + tail dgrad + ups + bt wgrad(2) + bt dgrad
         per_rcab = 2 + 2 + 1 + 2 + 1                            # ca_bwd(2) + wgrad(2) + dgrad + wgrad(2) + dgrad
-        grp = 2 + 1 + R * per_rcab + 1                          # gt wgrad(2) + gt dgrad + rcabs + ca param grads
+        grp = 2 + 1 + R * per_rcab + 2                          # gt wgrad(2) + gt dgrad + rcabs + ca param grads(2)
         return seg0 + G * grp + 2
 
     # -- forward / backward ---------------------------------------------------------------------

@@ -236,8 +236,10 @@ def test_channel_attention_forward_backward(env, B, H, W, red):
     # parameter gradients: one "layer" laid out as [w1,b1,w2,b2]
     flat = torch.cat([w1.flatten(), b1.flatten(), w2.flatten(), b2.flatten()])
     gflat = torch.full_like(flat, float("nan"))
+    lib.sres_ca_param_grads_scratch_bytes.restype = C.c_size_t
+    scr = torch.empty(lib.sres_ca_param_grads_scratch_bytes(1, B), dtype=torch.uint8, device=dev)
     L.check(lib.sres_ca_param_grads(ptr(flat), ptr(gflat), C.c_int64(flat.numel()), 1, ptr(mean), ptr(ds), B, hid, 0,
-                                    L.cur_stream()), "ca_param_grads")
+                                    ptr(scr), C.c_size_t(scr.numel()), L.cur_stream()), "ca_param_grads")
     torch.cuda.synchronize()
     ref_flat = torch.cat([sd[k].grad.flatten() for k in sd])
     assert rel_l2(gflat.cpu(), ref_flat) < 1e-4
