@@ -113,6 +113,18 @@ SRES_API int sres_pack_conv_weights(const float* w_oihw, void* out_bf16, int mod
 /*   workspace: at least sres_conv_wgrad_workspace_bytes() bytes of device memory              */
 /* ------------------------------------------------------------------------------------------ */
 SRES_API size_t sres_conv_wgrad_workspace_bytes(void);
+/* Several independent weight gradients of the same geometry in ONE launch (split-K CTAs are divided
+ * between the jobs; fewer partials per job, one prologue / accumulator drain per batch).            */
+#define SRES_WGRAD_MAX_JOBS 4
+typedef struct sres_wgrad_job {
+  const void* x_bf16;      /* conv input, bf16 PTL                                               */
+  const void* dy_bf16;     /* gradient of the conv output, bf16 PTL                              */
+  float* dw_oihw;          /* fp32 (cout_total, 64, 3, 3)                                        */
+  float* dbias;            /* fp32 (cout_total) or NULL                                          */
+  int32_t cout_total, oc_stride, oc_offset, accumulate;
+} sres_wgrad_job;
+SRES_API int sres_conv3x3_wgrad_batch(const sres_wgrad_job* jobs, int njobs, int B, int H, int W, void* workspace,
+                                      size_t workspace_bytes, void* stream);
 SRES_API int sres_conv3x3_wgrad(const void* x_bf16, const void* dy_bf16, int B, int H, int W, float* dw_oihw,
                                 float* dbias, int cout_total, int oc_stride, int oc_offset, int accumulate,
                                 void* workspace, size_t workspace_bytes, void* stream);

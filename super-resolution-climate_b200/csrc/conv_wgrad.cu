@@ -8,9 +8,12 @@
 // (off_b - off_a) rows, expressed through the descriptor's leading-dimension byte offset.  9 taps
 // -> 5 accumulators of 128 x 64 fp32 in TMEM (the last one carries one junk half).
 //
-// Each persistent CTA reduces its share of 128-position chunks and writes one fp32 partial
-// [5][128][64] (+ the bias-gradient partial, column sums of dY).  A second kernel sums the
-// partials in a fixed order (deterministic) and scatters them into the OIHW fp32 gradient.
+// Up to 4 independent weight gradients ("jobs": different layers of the backward pass) share one
+// launch: CTA c works on job c % njobs and reduces every nsplit-th 128-position chunk of it.  Fewer
+// split-K partials per job means less partial traffic and the per-launch cost (prologue, accumulator
+// drain) is paid once per batch.  Each CTA TMA-stores its fp32 partial [5][128][64] (+ the bias-gradient
+// partial, column sums of dY); a second kernel sums the partials in a fixed order (deterministic) and
+// scatters them into the OIHW fp32 gradient.
 //
 // Replaces the weight/bias part of aten::convolution_backward for the reference's nn.Conv2d
 // (sres/model/common/cnn.py:8-9), reached from mloss.backward() (dual_trainer.py:322).
@@ -21,17 +24,23 @@ namespace sres {
 
 constexpr int kWgMaxStages = 4;
 constexpr int kWgAcc = 5;
+constexpr int kWgMaxJobs = SRES_WGRAD_MAX_JOBS;
+constexpr int kWgPartFloats = kWgAcc * 128 * 64;  // one partial: [5][128][64]
+
+struct WgMaps {
+  CUtensorMap x[kWgMaxJobs];
+  CUtensorMap dy[kWgMaxJobs];
+};
 
 struct WgradKParams {
-  int P, npos, n_chunks, nstage, xrows;
+  int P, npos, n_chunks, nstage, xrows, njobs, max_split;
   int off_a[kWgAcc];   // row offset (ky*P+kx) of the first tap of each accumulator
   int lbo[kWgAcc];     // byte distance to the second tap's window
-  float* part;         // [grid][5*128*64 + 64]
+  float* part_bias;    // [njobs][max_split][64]
 };
 
 __global__ void __launch_bounds__(256, 1)
-conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
-                     const WgradKParams p) {
+conv3x3_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ CUtensorMap tmPart, const WgradKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = (128 + p.xrows) * 128;
@@ -44,10 +53,16 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction
   const int lane = threadIdx.x & 31;
+  // this CTA's job and its position among the CTAs of that job
+  const int job = blockIdx.x % p.njobs;
+  const int split = blockIdx.x / p.njobs;
+  const int nsplit = (int(gridDim.x) - job + p.njobs - 1) / p.njobs;
+  const CUtensorMap* tmX = &maps.x[job];
+  const CUtensorMap* tmDY = &maps.dy[job];
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmX);
-    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(tmX);
+    tma_prefetch_desc(tmDY);
     for (int i = 0; i < kWgMaxStages; ++i) {
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_empty[i], 1 + 4);  // MMA commit + 4 bias-gradient warps
@@ -66,64 +81,60 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 
   if (warp == 0) {
     const bool leader = elect_one();
-    {
-      int it = 0;
-      for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x, ++it) {
-        const int slot = it % p.nstage;
-        const uint32_t ph = (it / p.nstage) & 1;
-        mbar_wait(&bar_empty[slot], ph ^ 1, 11);
-        uint8_t* dst = smem + slot * stage_bytes;
-        const int q0 = c * 128;
-        if (leader) {
-          mbar_expect_tx(&bar_full[slot], stage_bytes);
-          tma_load_2d(dst, &tmDY, &bar_full[slot], 0, q0);
-          tma_load_2d(dst + 64 * 128, &tmDY, &bar_full[slot], 0, q0 + 64);
-          uint8_t* xdst = dst + 128 * 128;
-          const int x0 = q0 - (p.P + 1);
-          for (int r = 0; r < p.xrows; r += 64) tma_load_2d(xdst + r * 128, &tmX, &bar_full[slot], 0, x0 + r);
-        }
-        __syncwarp();
+    int it = 0;
+    for (int c = split; c < p.n_chunks; c += nsplit, ++it) {
+      const int slot = it % p.nstage;
+      const uint32_t ph = (it / p.nstage) & 1;
+      mbar_wait(&bar_empty[slot], ph ^ 1, 11);
+      uint8_t* dst = smem + slot * stage_bytes;
+      const int q0 = c * 128;
+      if (leader) {
+        mbar_expect_tx(&bar_full[slot], stage_bytes);
+        tma_load_2d(dst, tmDY, &bar_full[slot], 0, q0);
+        tma_load_2d(dst + 64 * 128, tmDY, &bar_full[slot], 0, q0 + 64);
+        uint8_t* xdst = dst + 128 * 128;
+        const int x0 = q0 - (p.P + 1);
+        for (int r = 0; r < p.xrows; r += 64) tma_load_2d(xdst + r * 128, tmX, &bar_full[slot], 0, x0 + r);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     const bool leader = elect_one();
-    {
-      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
-      constexpr uint32_t dhi = sdesc_hi_sw128(1024);
-      const uint32_t s_addr = smem_u32(smem);
-      uint32_t xoff[kWgAcc];
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+    constexpr uint32_t dhi = sdesc_hi_sw128(1024);
+    const uint32_t s_addr = smem_u32(smem);
+    uint32_t xoff[kWgAcc];
 #pragma unroll
-      for (int a = 0; a < kWgAcc; ++a) xoff[a] = uint32_t(p.off_a[a]) * 8 + ((uint32_t(p.lbo[a]) >> 4) << 16);
-      int it = 0;
-      for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x, ++it) {
-        const int slot = it % p.nstage;
-        const uint32_t ph = (it / p.nstage) & 1;
-        mbar_wait(&bar_full[slot], ph, 12);
-        tc_fence_after();
-        const uint32_t dy_lo = sdesc_lo(s_addr + slot * stage_bytes, 1024);
-        const uint32_t x_lo = sdesc_lo(s_addr + slot * stage_bytes + 128 * 128, 0);
+    for (int a = 0; a < kWgAcc; ++a) xoff[a] = uint32_t(p.off_a[a]) * 8 + ((uint32_t(p.lbo[a]) >> 4) << 16);
+    int it = 0;
+    for (int c = split; c < p.n_chunks; c += nsplit, ++it) {
+      const int slot = it % p.nstage;
+      const uint32_t ph = (it / p.nstage) & 1;
+      mbar_wait(&bar_full[slot], ph, 12);
+      tc_fence_after();
+      const uint32_t dy_lo = sdesc_lo(s_addr + slot * stage_bytes, 1024);
+      const uint32_t x_lo = sdesc_lo(s_addr + slot * stage_bytes + 128 * 128, 0);
+      if (leader) {
 #pragma unroll
         for (int a = 0; a < kWgAcc; ++a) {
           const uint32_t xa = x_lo + xoff[a];
-          if (leader) {
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-              if (kk == 0) umma_bf16_lohi_p(tmem_base + a * 64, xa, dhi, dy_lo, dhi, idesc, it ? 1u : 0u);
-              else umma_bf16_lohi<true>(tmem_base + a * 64, xa + kk * 128, dhi, dy_lo + kk * 128, dhi, idesc);
-            }
+          for (int kk = 0; kk < 8; ++kk) {
+            if (kk == 0) umma_bf16_lohi_p(tmem_base + a * 64, xa, dhi, dy_lo, dhi, idesc, it ? 1u : 0u);
+            else umma_bf16_lohi<true>(tmem_base + a * 64, xa + kk * 128, dhi, dy_lo + kk * 128, dhi, idesc);
           }
         }
-        __syncwarp();
-        if (leader) umma_commit(&bar_empty[slot]);
+        umma_commit(&bar_empty[slot]);
       }
-      if (leader) umma_commit(bar_done);
+      __syncwarp();
     }
+    if (leader) umma_commit(bar_done);
   } else if (warp >= 4) {
     // bias gradient: column sums of the dY tile, read straight from the swizzled smem rows.
     const int wq = warp & 3;
     float acc0 = 0.f, acc1 = 0.f;  // channels 2*lane, 2*lane+1 over rows wq*32 .. wq*32+31
     int it = 0;
-    for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x, ++it) {
+    for (int c = split; c < p.n_chunks; c += nsplit, ++it) {
       const int slot = it % p.nstage;
       const uint32_t ph = (it / p.nstage) & 1;
       mbar_wait(&bar_full[slot], ph, 13);
@@ -141,76 +152,107 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
     s_db[wq * 64 + 2 * lane] = acc0;
     s_db[wq * 64 + 2 * lane + 1] = acc1;
-    // drain the accumulators
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // all four warps are done reading the operand ring
+    // drain the accumulators: TMEM -> swizzled smem slab (the operand ring is idle now) -> TMA store
     mbar_wait(bar_done, 0, 14);
     tc_fence_after();
-    float* out = p.part + (size_t)blockIdx.x * (kWgAcc * 128 * 64 + 64);
-    const int m = wq * 32 + lane;
+    uint8_t* slab = smem + wq * 8192;  // [2 halves][32 rows x 128 B]
+    const int sw7 = lane & 7;
+    const int prow0 = ((job * p.max_split + split) * kWgAcc) * 128 + wq * 32;  // row of the partial matrix
     for (int a = 0; a < kWgAcc; ++a) {
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t raw[16];
-        tmem_ld16(tmem_base + (uint32_t(wq * 32) << 16) + a * 64 + ch * 16, raw);
-        tmem_ld_wait();
-        float4* op = reinterpret_cast<float4*>(out + ((size_t)a * 128 + m) * 64 + ch * 16);
+      if (lane == 0) bulk_wait_read<0>();
+      __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          op[j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
-                              __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
+      for (int h = 0; h < 2; ++h) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + (uint32_t(wq * 32) << 16) + a * 64 + h * 32, raw);
+        tmem_ld_wait();
+        uint8_t* row = slab + h * 4096 + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(row + ((j ^ sw7) << 4)) =
+              make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]), __uint_as_float(raw[4 * j + 2]),
+                          __uint_as_float(raw[4 * j + 3]));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tmPart, slab, 0, prow0 + a * 128);
+        tma_store_2d(&tmPart, slab + 4096, 32, prow0 + a * 128);
+        bulk_commit();
       }
     }
+    if (lane == 0) bulk_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x < 64) {
-    float* out = p.part + (size_t)blockIdx.x * (kWgAcc * 128 * 64 + 64) + kWgAcc * 128 * 64;
+    float* out = p.part_bias + ((size_t)job * p.max_split + split) * 64;
     out[threadIdx.x] = s_db[threadIdx.x] + s_db[64 + threadIdx.x] + s_db[128 + threadIdx.x] + s_db[192 + threadIdx.x];
   }
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-// Sum the per-CTA partials in CTA order and scatter into the OIHW gradient.
+// Sum the per-CTA partials in split order and scatter into the OIHW gradient.
 //   accumulator a, row m = half*64 + ci, column n = co   ->  tap = 2a + half (a < 4), tap 8 for a == 4 half 0
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int nparts, float* __restrict__ dw,
-                                    float* __restrict__ db, int cout_total, int oc_stride, int oc_offset,
-                                    int accumulate) {
+struct WgReduceJob {
+  float* dw;
+  float* db;
+  int cout_total, oc_stride, oc_offset, accumulate, nsplit;
+};
+struct WgReduceJobs {
+  WgReduceJob j[kWgMaxJobs];
+};
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ part_bias, int max_split,
+                                    const __grid_constant__ WgReduceJobs jobs) {
+  const int job = blockIdx.y;
+  const WgReduceJob& J = jobs.j[job];
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int stride = kWgAcc * 128 * 64 + 64;
-  if (idx >= stride) return;
-  float s = 0.f;
-  for (int i = 0; i < nparts; ++i) s += part[(size_t)i * stride + idx];
-  if (idx >= kWgAcc * 128 * 64) {
-    const int co = idx - kWgAcc * 128 * 64;
-    const int oc = co * oc_stride + oc_offset;
-    if (db && oc < cout_total) db[oc] = accumulate ? db[oc] + s : s;
+  if (idx >= kWgPartFloats + 64) return;
+  if (idx >= kWgPartFloats) {
+    const int co = idx - kWgPartFloats;
+    float s = 0.f;
+    for (int i = 0; i < J.nsplit; ++i) s += part_bias[((size_t)job * max_split + i) * 64 + co];
+    const int oc = co * J.oc_stride + J.oc_offset;
+    if (J.db && oc < J.cout_total) J.db[oc] = J.accumulate ? J.db[oc] + s : s;
     return;
   }
+  float s = 0.f;
+  const float* pp = part + (size_t)job * max_split * kWgPartFloats + idx;
+  for (int i = 0; i < J.nsplit; ++i) s += pp[(size_t)i * kWgPartFloats];
   const int n = idx & 63;
   const int m = (idx >> 6) & 127;
   const int a = idx >> 13;
   const int half = m >> 6, ci = m & 63;
   const int tap = 2 * a + half;
   if (tap > 8) return;
-  const int oc = n * oc_stride + oc_offset;
-  if (oc >= cout_total) return;
-  float* o = dw + ((size_t)oc * 64 + ci) * 9 + tap;
-  *o = accumulate ? *o + s : s;
+  const int oc = n * J.oc_stride + J.oc_offset;
+  if (oc >= J.cout_total) return;
+  float* o = J.dw + ((size_t)oc * 64 + ci) * 9 + tap;
+  *o = J.accumulate ? *o + s : s;
+}
+
+static int wg_grid() {
+  int sms = device_sm_count();
+  return sms > 0 ? sms : 148;
 }
 
 }  // namespace sres
 
+using namespace sres;
+
 extern "C" size_t sres_conv_wgrad_workspace_bytes(void) {
-  int sms = sres::device_sm_count();
-  if (sms <= 0) sms = 148;
-  return (size_t)sms * (sres::kWgAcc * 128 * 64 + 64) * sizeof(float);
+  // partial matrix for a full grid of CTAs (+ one spare per job for rounding) and the bias partials
+  const size_t slots = (size_t)wg_grid() + kWgMaxJobs;
+  return slots * kWgPartFloats * sizeof(float) + slots * 64 * sizeof(float) + 1024;
 }
 
-extern "C" int sres_conv3x3_wgrad(const void* x_bf16, const void* dy_bf16, int B, int H, int W, float* dw_oihw,
-                                  float* dbias, int cout_total, int oc_stride, int oc_offset, int accumulate,
-                                  void* workspace, size_t workspace_bytes, void* stream_) {
-  using namespace sres;
+extern "C" int sres_conv3x3_wgrad_batch(const sres_wgrad_job* jobs, int njobs, int B, int H, int W, void* workspace,
+                                        size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (!x_bf16 || !dy_bf16 || !dw_oihw || !workspace) return set_error(SRES_ERR_INVALID_ARG, "wgrad: null pointer");
+  if (!jobs || njobs < 1 || njobs > kWgMaxJobs) return set_error(SRES_ERR_INVALID_ARG, "wgrad: 1..4 jobs per batch");
+  if (!workspace) return set_error(SRES_ERR_INVALID_ARG, "wgrad: null workspace");
   if (B <= 0 || H <= 0 || W <= 0) return set_error(SRES_ERR_INVALID_ARG, "wgrad: bad geometry");
   WgradKParams p{};
   p.P = W + 1;
@@ -223,6 +265,7 @@ extern "C" int sres_conv3x3_wgrad(const void* x_bf16, const void* dy_bf16, int B
   int nstage = (232448 - 1024 - 2048) / stage_bytes;
   if (nstage > kWgMaxStages) nstage = kWgMaxStages;
   if (nstage < 1) return set_error(SRES_ERR_UNSUPPORTED, "wgrad: image too wide for the flat halo window");
+  if (nstage * stage_bytes < 32768) return set_error(SRES_ERR_UNSUPPORTED, "wgrad: operand ring smaller than the drain slabs");
   p.nstage = nstage;
   for (int a = 0; a < kWgAcc; ++a) {
     const int ta = 2 * a, tb = (2 * a + 1 <= 8) ? 2 * a + 1 : -1;
@@ -231,25 +274,51 @@ extern "C" int sres_conv3x3_wgrad(const void* x_bf16, const void* dy_bf16, int B
     p.lbo[a] = tb >= 0 ? (((tb / 3) * p.P + (tb % 3)) - offa) * 128 : 128;
     if (p.lbo[a] >= (1 << 18)) return set_error(SRES_ERR_UNSUPPORTED, "wgrad: tap distance exceeds descriptor range");
   }
-  int sms = device_sm_count();
+  const int sms = device_sm_count();
   if (sms <= 0) return set_error(SRES_ERR_NO_DEVICE, "wgrad: no CUDA device");
-  const int grid = p.n_chunks < sms ? p.n_chunks : sms;
-  const size_t need = (size_t)grid * (kWgAcc * 128 * 64 + 64) * sizeof(float);
-  if (workspace_bytes < need) return set_error(SRES_ERR_INVALID_ARG, "wgrad: workspace too small");
-  p.part = (float*)workspace;
-  CUtensorMap tmX, tmDY;
-  int rc = make_tmap_rows64(&tmX, x_bf16, (uint64_t)p.npos, 64);
-  if (rc) return rc;
-  rc = make_tmap_rows64(&tmDY, dy_bf16, (uint64_t)p.npos, 64);
+  int grid = sms;
+  if (grid > p.n_chunks * njobs) grid = p.n_chunks * njobs;
+  if (grid < njobs) grid = njobs;
+  p.njobs = njobs;
+  p.max_split = (grid + njobs - 1) / njobs;
+  const size_t part_bytes = (size_t)njobs * p.max_split * kWgPartFloats * sizeof(float);
+  const size_t bias_bytes = (size_t)njobs * p.max_split * 64 * sizeof(float);
+  if (workspace_bytes < part_bytes + bias_bytes) return set_error(SRES_ERR_INVALID_ARG, "wgrad: workspace too small");
+  float* part = (float*)workspace;
+  p.part_bias = (float*)((uint8_t*)workspace + part_bytes);
+
+  WgMaps maps;
+  WgReduceJobs rj;
+  for (int j = 0; j < kWgMaxJobs; ++j) {
+    const sres_wgrad_job& J = jobs[j < njobs ? j : 0];
+    if (!J.x_bf16 || !J.dy_bf16 || !J.dw_oihw) return set_error(SRES_ERR_INVALID_ARG, "wgrad: null pointer in job");
+    int rc = make_tmap_rows64(&maps.x[j], J.x_bf16, (uint64_t)p.npos, 64);
+    if (rc) return rc;
+    rc = make_tmap_rows64(&maps.dy[j], J.dy_bf16, (uint64_t)p.npos, 64);
+    if (rc) return rc;
+    rj.j[j].dw = J.dw_oihw; rj.j[j].db = J.dbias; rj.j[j].cout_total = J.cout_total; rj.j[j].oc_stride = J.oc_stride;
+    rj.j[j].oc_offset = J.oc_offset; rj.j[j].accumulate = J.accumulate;
+    rj.j[j].nsplit = j < njobs ? (grid - j + njobs - 1) / njobs : 0;
+  }
+  CUtensorMap tmPart;
+  int rc = make_tmap_rows64_f32(&tmPart, part, (uint64_t)njobs * p.max_split * kWgAcc * 128, 32);
   if (rc) return rc;
   const size_t smem = (size_t)nstage * stage_bytes + 1024 + 2048;
   cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_cuda_error(e, "wgrad: smem attribute");
-  conv3x3_wgrad_kernel<<<grid, 256, smem, stream>>>(tmX, tmDY, p);
+  conv3x3_wgrad_kernel<<<grid, 256, smem, stream>>>(maps, tmPart, p);
   SRES_CHECK_LAUNCH("wgrad: launch");
-  const int total = kWgAcc * 128 * 64 + 64;
-  wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(p.part, grid, dw_oihw, dbias, cout_total, oc_stride,
-                                                               oc_offset, accumulate);
+  const int total = kWgPartFloats + 64;
+  wgrad_reduce_kernel<<<dim3((total + 255) / 256, njobs), 256, 0, stream>>>(part, p.part_bias, p.max_split, rj);
   SRES_CHECK_LAUNCH("wgrad: reduce launch");
   return SRES_OK;
+}
+
+extern "C" int sres_conv3x3_wgrad(const void* x_bf16, const void* dy_bf16, int B, int H, int W, float* dw_oihw,
+                                  float* dbias, int cout_total, int oc_stride, int oc_offset, int accumulate,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  sres_wgrad_job j;
+  j.x_bf16 = x_bf16; j.dy_bf16 = dy_bf16; j.dw_oihw = dw_oihw; j.dbias = dbias;
+  j.cout_total = cout_total; j.oc_stride = oc_stride; j.oc_offset = oc_offset; j.accumulate = accumulate;
+  return sres_conv3x3_wgrad_batch(&j, 1, B, H, W, workspace, workspace_bytes, stream);
 }

@@ -31,7 +31,7 @@ struct Net {
   size_t o_wp_fwd, o_wp_dg, o_wp_up_fwd[4], o_wp_up_dg[4], o_wp_tail, o_bias_up[4], o_bias_tail;
   size_t o_xb, o_t1, o_t2, o_mean, o_s, o_ds, o_resb, o_u[4];
   size_t o_hf, o_gf[2], o_xf, o_pool_part, o_pool_sum;
-  size_t o_ga, o_gb32, o_gb16, o_dt2, o_dt1, o_ds_part, o_wg_ws, o_sw_ws, o_ca_scr, o_du16[4], o_du32[4], o_dres32, o_dres16;
+  size_t o_ga, o_gb32, o_gb16, o_dt2[3], o_dt1[3], o_ds_part, o_wg_ws, o_sw_ws, o_ca_scr, o_du16[4], o_du32[4], o_dres32, o_dres16;
   size_t total;
   int n_xb, n_t;  // saved-buffer counts (1 in inference mode)
   long long cidx(int g, int r, int which) const { return (long long)g * (2 * d.n_blocks + 1) + 2 * r + which; }
@@ -117,8 +117,7 @@ static int build_net(Net* n, const sres_rcan_desc* d, int training) {
     n->o_ga = take(f32);
     n->o_gb32 = take(f32);
     n->o_gb16 = take(bf);
-    n->o_dt2 = take(bf);
-    n->o_dt1 = take(bf);
+    for (int k = 0; k < 3; ++k) { n->o_dt2[k] = take(bf); n->o_dt1[k] = take(bf); }
     const int bpi = sres_ca_blocks_per_image(d->B, d->H, d->W);
     n->o_ds_part = take((size_t)d->B * (bpi > 0 ? bpi : 1) * 64 * 4);
     n->o_wg_ws = take(sres_conv_wgrad_workspace_bytes());
@@ -289,11 +288,38 @@ static int forward(const Net& n, const float* P, const float* x, float* out, uin
 // backward.  Segments: 0 = tail conv, upsampler, body-tail conv; 1..G = residual groups G-1..0;
 // G+1 = head conv.  A caller overlapping the gradient all-reduce runs them one at a time.
 // ---------------------------------------------------------------------------------------------
-static int wgrad64(const void* x, const void* dy, int B, int H, int W, float* dw, float* db, int cout_total, int stride,
-                   int offset, int acc, const Net& n, uint8_t* ws, void* st) {
-  return sres_conv3x3_wgrad(x, dy, B, H, W, dw, db, cout_total, stride, offset, acc, ws + n.o_wg_ws,
-                            sres_conv_wgrad_workspace_bytes(), st);
-}
+// Deferred weight-gradient jobs: up to 4 of the same geometry go out as one batched launch.  A job only
+// reads saved activations and a bf16 output-gradient buffer; the queue is flushed before any kernel that
+// overwrites such a buffer is enqueued, when it is full, and at the end of every backward segment.
+struct WgQueue {
+  sres_wgrad_job jobs[SRES_WGRAD_MAX_JOBS];
+  int n = 0, B = 0, H = 0, W = 0;
+  const Net* net = nullptr;
+  uint8_t* ws = nullptr;
+  void* st = nullptr;
+  int flush() {
+    if (n == 0) return SRES_OK;
+    const int rc = sres_conv3x3_wgrad_batch(jobs, n, B, H, W, ws + net->o_wg_ws, sres_conv_wgrad_workspace_bytes(), st);
+    n = 0;
+    return rc;
+  }
+  int push(const void* x, const void* dy, int B_, int H_, int W_, float* dw, float* db, int cout_total, int stride,
+           int offset, int acc) {
+    if (n && (B_ != B || H_ != H || W_ != W)) RC(flush());
+    B = B_; H = H_; W = W_;
+    sres_wgrad_job& j = jobs[n++];
+    j.x_bf16 = x; j.dy_bf16 = dy; j.dw_oihw = dw; j.dbias = db;
+    j.cout_total = cout_total; j.oc_stride = stride; j.oc_offset = offset; j.accumulate = acc;
+    if (n == SRES_WGRAD_MAX_JOBS) RC(flush());
+    return SRES_OK;
+  }
+  // call before enqueuing a kernel that writes `buf`
+  int before_write(const void* buf) {
+    for (int i = 0; i < n; ++i)
+      if (jobs[i].dy_bf16 == buf) return flush();
+    return SRES_OK;
+  }
+};
 
 static int backward(const Net& n, const float* P, const float* x, const float* dout, float* Gr, int accumulate,
                     uint8_t* ws, int seg_begin, int seg_end, void* st) {
@@ -307,8 +333,8 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
   float* ga = (float*)(ws + n.o_ga);
   float* gb32 = (float*)(ws + n.o_gb32);
   void* gb16 = ws + n.o_gb16;
-  void* dt2 = ws + n.o_dt2;
-  void* dt1 = ws + n.o_dt1;
+  WgQueue wq;
+  wq.net = &n; wq.ws = ws; wq.st = st;
   float* dres32 = (float*)(ws + n.o_dres32);
   void* dres16 = ws + n.o_dres16;
   const int xb_last = G * (R + 1);  // bf16 copy of the last group's output = body-tail conv input
@@ -336,21 +362,22 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
         const int sf = i > 0 ? d.up_factor[i - 1] : 2;
         for (int sub = 0; sub < f2; ++sub) {
           const void* dy = ws + n.o_du16[i] + sub * sub_bytes;
-          RC(wgrad64(cur_in, dy, B, n.lvH[i], n.lvW[i], Gr + n.up_w[i], Gr + n.up_b[i], f2 * 64, f2, sub, accumulate, n,
-                     ws, st));
+          RC(wq.push(cur_in, dy, B, n.lvH[i], n.lvW[i], Gr + n.up_w[i], Gr + n.up_b[i], f2 * 64, f2, sub, accumulate));
           RC(conv64(dy, ws + n.o_wp_up_dg[i] + (size_t)sub * kConvW * 2, nullptr, B, n.lvH[i], n.lvW[i], st, acc32,
                     sub == f2 - 1 ? acc16 : nullptr, 0, nullptr, sub > 0 ? acc32 : nullptr, nullptr, nullptr, map, 0, 0,
                     sf));
         }
       }
       // body-tail conv
-      RC(wgrad64(XB(xb_last), dres16, B, H, W, Gr + n.bt_w, Gr + n.bt_b, 64, 1, 0, accumulate, n, ws, st));
+      RC(wq.push(XB(xb_last), dres16, B, H, W, Gr + n.bt_w, Gr + n.bt_b, 64, 1, 0, accumulate));
+      RC(wq.before_write(gb16));
       RC(conv64(dres16, WD(n.cidx_bt()), nullptr, B, H, W, st, ga, gb16));
+      RC(wq.flush());
     } else if (seg <= G) {
       const int g = G - seg;
       const int xb0 = g * (R + 1);  // XB index of the group's input
       float* Gg = Gr + n.off_gt(g);
-      RC(wgrad64(XB(xb0 + R), gb16, B, H, W, Gg, Gg + kConvW, 64, 1, 0, accumulate, n, ws, st));
+      RC(wq.push(XB(xb0 + R), gb16, B, H, W, Gg, Gg + kConvW, 64, 1, 0, accumulate));
       RC(conv64(gb16, WD(n.cidx_gt(g)), nullptr, B, H, W, st, gb32, nullptr));
       for (int r = R - 1; r >= 0; --r) {
         const int ti = g * R + r;
@@ -362,17 +389,23 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
         const float* b2 = w2 + 64 * n.hid;
         const float* mean = (const float*)(ws + n.o_mean) + (size_t)ti * B * 64;
         float* dsv = (float*)(ws + n.o_ds) + (size_t)ti * B * 64;
+        void* dt2 = ws + n.o_dt2[ti % 3];
+        void* dt1 = ws + n.o_dt1[ti % 3];
+        RC(wq.before_write(dt2));
         RC(sres_ca_bwd(gb32, T2(ti), w1, b1, w2, b2, n.hid, mean, (float*)(ws + n.o_ds_part), dt2, dsv, B, H, W, st));
-        RC(wgrad64(T1(ti), dt2, B, H, W, gr + kConvW + 64, gr + 2 * kConvW + 64, 64, 1, 0, accumulate, n, ws, st));
+        RC(wq.push(T1(ti), dt2, B, H, W, gr + kConvW + 64, gr + 2 * kConvW + 64, 64, 1, 0, accumulate));
+        RC(wq.before_write(dt1));
         RC(conv64(dt2, WD(n.cidx(g, r, 1)), nullptr, B, H, W, st, nullptr, dt1, 0, nullptr, nullptr, nullptr, T1(ti)));
-        RC(wgrad64(XB(xb0 + r), dt1, B, H, W, gr, gr + kConvW, 64, 1, 0, accumulate, n, ws, st));
+        RC(wq.push(XB(xb0 + r), dt1, B, H, W, gr, gr + kConvW, 64, 1, 0, accumulate));
         if (r > 0) {
           RC(conv64(dt1, WD(n.cidx(g, r, 0)), nullptr, B, H, W, st, gb32, nullptr, 0, nullptr, gb32));
         } else {
           // grad wrt the group input = body path (gb32 + conv1 dgrad) + group skip (ga)
+          RC(wq.before_write(gb16));
           RC(conv64(dt1, WD(n.cidx(g, r, 0)), nullptr, B, H, W, st, ga, gb16, 0, nullptr, gb32, ga));
         }
       }
+      RC(wq.flush());
       const long long first = n.off_rcab(g, 0) + 2 * (kConvW + 64);
       RC(sres_ca_param_grads(P + first, Gr + first, n.rcab_sz, R, (const float*)(ws + n.o_mean) + (size_t)g * R * B * 64,
                              (const float*)(ws + n.o_ds) + (size_t)g * R * B * 64, B, n.hid, accumulate, ws + n.o_ca_scr,

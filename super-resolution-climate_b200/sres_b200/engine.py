@@ -140,11 +140,14 @@ class RcanEngine:
         return 1 + G * (R * per_rcab + 1) + 1 + sum(f * f for f in self.stages) + 1
 
     def launches_backward(self) -> int:
+        """Kernels enqueued by one full backward (weight-gradient jobs go out in batches of <= 4: one
+        tensor-core kernel + one reduce kernel per batch)."""
         G, R = self.nlayers, self.nblocks
-        ups = sum(f * f * 3 for f in self.stages)             # wgrad + reduce + dgrad per sub-conv
-        seg0 = 2 + 1 + ups + 2 + 1                              # tail wgrad(2) + tail dgrad + ups + bt wgrad(2) + bt dgrad
-        per_rcab = 2 + 2 + 1 + 2 + 1                            # ca_bwd(2) + wgrad(2) + dgrad + wgrad(2) + dgrad
-        grp = 2 + 1 + R * per_rcab + 2                          # gt wgrad(2) + gt dgrad + rcabs + ca param grads(2)
+        ups_dgrad = sum(f * f for f in self.stages)
+        seg0_batches = sum(-(-f * f // 4) for f in self.stages) + 1      # per upsampler stage + body-tail conv
+        seg0 = 2 + 1 + ups_dgrad + 1 + 2 * seg0_batches                   # tail wgrad(2), tail dgrad, dgrads, bt dgrad
+        grp_batches = -(-(1 + 2 * R) // 4)
+        grp = 1 + R * (2 + 1 + 1) + 2 + 2 * grp_batches                   # gt dgrad, per RCAB ca_bwd(2)+2 dgrads, ca params(2)
         return seg0 + G * grp + 2
 
     # -- forward / backward ---------------------------------------------------------------------
