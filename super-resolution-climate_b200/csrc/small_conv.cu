@@ -17,62 +17,66 @@ constexpr int kMaxSmallC = 4;
 // planar (B,Cs,H,W) fp32  ->  PTL [rows][64]
 //   transposed == 0:  w is (64, Cs, 3, 3):  out[q][n] = b[n] + sum_{c,t} w[n][c][t] * in[c][q+off(t)]
 //   transposed == 1:  w is (Cs, 64, 3, 3):  out[q][n] =        sum_{c,t} w[c][n][8-t] * in[c][q+off(t)]
-// One thread = one position x 8 output features.  Padding rows are written as zeros.
+// A block owns a band of kBandRows image rows of one image: the planar input band (+1 row/column halo,
+// zero outside the image) is staged in shared memory once; a thread owns 2 output features (its 2*Cs*9
+// weights live in registers) and walks the band's PTL rows, so a warp writes one full 128-byte bf16 row
+// (256-byte fp32 row) per position.  Padding rows (x == W, y == H) are written as zeros.
 // ---------------------------------------------------------------------------------------------
+constexpr int kBandRows = 8;
+
+template <int CS>
 __global__ void __launch_bounds__(256)
 conv3x3_small_in_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
-                        int B, int Cs, int H, int W, int transposed, int unshuffle, float* __restrict__ out_f32,
+                        int B, int H, int W, int transposed, int unshuffle, float* __restrict__ out_f32,
                         uint16_t* __restrict__ out_bf16) {
-  __shared__ float sw[64 * kMaxSmallC * 9];  // [n][c][t]
-  __shared__ float sb[64];
-  for (int i = threadIdx.x; i < 64 * Cs * 9; i += blockDim.x) {
-    const int t = i % 9, c = (i / 9) % Cs, n = i / (9 * Cs);
-    sw[i] = transposed ? w[(c * 64 + n) * 9 + (8 - t)] : w[(n * Cs + c) * 9 + t];
+  extern __shared__ float s_in[];  // [CS][kBandRows+2][W+2]
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int n0 = lane * 2;  // two output features
+  float wr[2][CS * 9], br[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    br[j] = (bias && !transposed) ? bias[n0 + j] : 0.f;
+#pragma unroll
+    for (int c = 0; c < CS; ++c)
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+        wr[j][c * 9 + t] = transposed ? w[(c * 64 + n0 + j) * 9 + (8 - t)] : w[((n0 + j) * CS + c) * 9 + t];
   }
-  if (threadIdx.x < 64) sb[threadIdx.x] = (bias && !transposed) ? bias[threadIdx.x] : 0.f;
-  __syncthreads();
-  const int P = W + 1, RP = (H + 1) * P;
-  const long long total = (long long)B * RP * 8;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int cg = int(idx & 7);
-    const long long q = idx >> 3;
-    const int b = int(q / RP), rem = int(q - (long long)b * RP);
-    const int y = rem / P, x = rem - y * P;
-    float acc[8];
+  const int P = W + 1, RP = (H + 1) * P, SW = W + 2;
+  const int bands = (H + 1 + kBandRows - 1) / kBandRows;  // the zero row y == H belongs to the last band
+  for (int item = blockIdx.x; item < B * bands; item += gridDim.x) {
+    const int b = item / bands, y0 = (item % bands) * kBandRows;
+    __syncthreads();
+    for (int i = threadIdx.x; i < CS * (kBandRows + 2) * SW; i += blockDim.x) {
+      const int xx = i % SW - 1, yy = (i / SW) % (kBandRows + 2) + y0 - 1, c = i / (SW * (kBandRows + 2));
+      s_in[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(in + (((size_t)b * CS + c) * H + yy) * W + xx) : 0.f;
+    }
+    __syncthreads();
+    const int rows = min(kBandRows, H + 1 - y0);
+    for (int pos = wrp; pos < rows * P; pos += 8) {
+      const int yl = pos / P, x = pos - yl * P, y = y0 + yl;
+      float a0 = 0.f, a1 = 0.f;
+      if (x != W && y != H) {
+        a0 = br[0]; a1 = br[1];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    const bool pad = (x == W) || (y == H);
-    if (!pad) {
+        for (int c = 0; c < CS; ++c)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = sb[cg * 8 + j];
-      for (int c = 0; c < Cs; ++c) {
-        const float* ip = in + ((size_t)b * Cs + c) * H * W;
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-          if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-          const float v = __ldg(ip + (size_t)yy * W + xx);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(sw[((cg * 8 + j) * Cs + c) * 9 + t], v, acc[j]);
-        }
+          for (int t = 0; t < 9; ++t) {
+            const float v = s_in[(c * (kBandRows + 2) + yl + t / 3) * SW + x + t % 3];
+            a0 = fmaf(wr[0][c * 9 + t], v, a0);
+            a1 = fmaf(wr[1][c * 9 + t], v, a1);
+          }
       }
+      long long oq = (long long)b * RP + (long long)y * P + x;
+      if (unshuffle > 1) {  // PixelUnshuffle(f) store: sub-grid (y%f, x%f), position (y/f, x/f)
+        const int f = unshuffle;
+        const int Pl = W / f + 1, Rl = H / f + 1;
+        const int sub = (y % f) * f + (x % f);
+        oq = (long long)sub * B * Rl * Pl + (long long)b * Rl * Pl + (long long)(y / f) * Pl + (x / f);
+      }
+      if (out_f32) *reinterpret_cast<float2*>(out_f32 + oq * 64 + n0) = make_float2(a0, a1);
+      if (out_bf16) *reinterpret_cast<uint32_t*>(out_bf16 + oq * 64 + n0) = pack_bf16x2(a0, a1);
     }
-    long long oq = q;
-    if (unshuffle > 1) {  // PixelUnshuffle(f) store: sub-grid (y%f, x%f), position (y/f, x/f)
-      const int f = unshuffle;
-      const int Pl = W / f + 1, Rl = H / f + 1;
-      const int sub = (y % f) * f + (x % f);
-      oq = (long long)sub * B * Rl * Pl + (long long)b * Rl * Pl + (long long)(y / f) * Pl + (x / f);
-    }
-    if (out_f32) {
-      *reinterpret_cast<float4*>(out_f32 + oq * 64 + cg * 8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      *reinterpret_cast<float4*>(out_f32 + oq * 64 + cg * 8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    }
-    if (out_bf16)
-      *reinterpret_cast<uint4*>(out_bf16 + oq * 64 + cg * 8) =
-          make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
-                     pack_bf16x2(acc[6], acc[7]));
   }
 }
 
@@ -137,43 +141,68 @@ __global__ void small_in_wgrad_reduce_kernel(const float* __restrict__ part, int
 // tail-conv weight gradient: dW[c][k][t] = sum_q dout[c][q] * U[q+off(t)][k],  db[c] = sum_q dout[c][q]
 // Looping over the rows p of U and scattering to the 9 taps reads U once:
 //   dW[c][k][t] += U[p][k] * dout[c][p - off(t)].
-// block = 64 input features x 4 row lanes.
+// A block owns bands of kBandRows image rows: the planar dout band (+halo, zero outside) is staged in
+// shared memory; a thread owns 2 input features k (one bf16x2 load per U row, a warp reads one full
+// 128-byte row) and 8 warps walk the band's rows.  Per-block partials, then a fixed-order reduce.
 // ---------------------------------------------------------------------------------------------
+template <int CS>
 __global__ void __launch_bounds__(256)
-small_out_wgrad_kernel(const float* __restrict__ dout, const uint16_t* __restrict__ u, int B, int Cs, int H, int W,
+small_out_wgrad_kernel(const float* __restrict__ dout, const uint16_t* __restrict__ u, int B, int H, int W,
                        float* __restrict__ part) {
-  __shared__ float sm[4][64][kSwAcc];
-  const int k = threadIdx.x & 63, ln = threadIdx.x >> 6;
-  const int P = W + 1, RP = (H + 1) * P;
-  const long long npos = (long long)B * RP;
-  float acc[kSwAcc];
+  extern __shared__ float s_d[];  // [CS][kBandRows+2][W+2], then the cross-warp reduction buffer
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int k0 = lane * 2;
+  const int P = W + 1, RP = (H + 1) * P, SW = W + 2;
+  float acc[2][CS * 9];
+  float accb = 0.f;  // bias gradient: lanes < CS of warp 0..7 sum channel `lane`
 #pragma unroll
-  for (int i = 0; i < kSwAcc; ++i) acc[i] = 0.f;
-  for (long long q = (long long)blockIdx.x * 4 + ln; q < npos; q += (long long)gridDim.x * 4) {
-    const int b = int(q / RP), rem = int(q - (long long)b * RP);
-    const int y = rem / P, x = rem - y * P;
-    if (x == W || y == H) continue;
-    const uint16_t raw = u[q * 64 + k];
-    const float uv = __uint_as_float(uint32_t(raw) << 16);
-    for (int c = 0; c < Cs; ++c) {
-      const float* dp = dout + ((size_t)b * Cs + c) * H * W;
+  for (int j = 0; j < 2; ++j)
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        // output pixel that sees row p through tap t:  (y,x) - (t/3-1, t%3-1)
-        const int yy = y - (t / 3 - 1), xx = x - (t % 3 - 1);
-        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-        acc[c * 9 + t] = fmaf(uv, __ldg(dp + (size_t)yy * W + xx), acc[c * 9 + t]);
-      }
+    for (int i = 0; i < CS * 9; ++i) acc[j][i] = 0.f;
+  const int bands = (H + kBandRows - 1) / kBandRows;
+  for (int item = blockIdx.x; item < B * bands; item += gridDim.x) {
+    const int b = item / bands, y0 = (item % bands) * kBandRows;
+    __syncthreads();
+    for (int i = threadIdx.x; i < CS * (kBandRows + 2) * SW; i += blockDim.x) {
+      const int xx = i % SW - 1, yy = (i / SW) % (kBandRows + 2) + y0 - 1, c = i / (SW * (kBandRows + 2));
+      s_d[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(dout + (((size_t)b * CS + c) * H + yy) * W + xx) : 0.f;
     }
-    // bias gradient: feature lane k < Cs sums its own output channel
-    if (k < Cs) acc[kSwAcc - 1] += __ldg(dout + ((size_t)b * Cs + k) * H * W + (size_t)y * W + x);
-  }
+    __syncthreads();
+    const int rows = min(kBandRows, H - y0);
+    for (int pos = wrp; pos < rows * W; pos += 8) {
+      const int yl = pos / W, x = pos - yl * W;
+      const size_t q = (size_t)b * RP + (size_t)(y0 + yl) * P + x;
+      const uint32_t uv = *reinterpret_cast<const uint32_t*>(u + q * 64 + k0);
+      const float u0 = bf16_lo(uv), u1 = bf16_hi(uv);
 #pragma unroll
-  for (int i = 0; i < kSwAcc; ++i) sm[ln][k][i] = acc[i];
+      for (int c = 0; c < CS; ++c)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          // output pixel that sees row p through tap t: (y,x) - (t/3-1, t%3-1); smem index shifts by +1 halo
+          const float d = s_d[(c * (kBandRows + 2) + yl + 2 - t / 3) * SW + x + 2 - t % 3];
+          acc[0][c * 9 + t] = fmaf(u0, d, acc[0][c * 9 + t]);
+          acc[1][c * 9 + t] = fmaf(u1, d, acc[1][c * 9 + t]);
+        }
+      if (lane < CS) accb += s_d[(lane * (kBandRows + 2) + yl + 1) * SW + x + 1];
+    }
+  }
+  // cross-warp reduction through shared memory: [8 warps][64 k][kSwAcc]
+  __syncthreads();
+  float* red = s_d;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+#pragma unroll
+    for (int i = 0; i < CS * 9; ++i) red[(wrp * 64 + k0 + j) * kSwAcc + i] = acc[j][i];
+    for (int i = CS * 9; i < kSwAcc; ++i) red[(wrp * 64 + k0 + j) * kSwAcc + i] = 0.f;
+  }
+  __syncthreads();
+  if (lane < CS) red[(wrp * 64 + lane) * kSwAcc + kSwAcc - 1] = accb;
   __syncthreads();
   for (int i = threadIdx.x; i < 64 * kSwAcc; i += 256) {
-    const int kk = i / kSwAcc, e = i % kSwAcc;
-    part[(size_t)blockIdx.x * 64 * kSwAcc + i] = sm[0][kk][e] + sm[1][kk][e] + sm[2][kk][e] + sm[3][kk][e];
+    float sum = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) sum += red[ww * 64 * kSwAcc + i];
+    part[(size_t)blockIdx.x * 64 * kSwAcc + i] = sum;
   }
 }
 
@@ -211,12 +240,26 @@ extern "C" int sres_conv3x3_small_in(const float* in_nchw, const float* w, const
   if (B <= 0 || H <= 0 || W <= 0) return set_error(SRES_ERR_INVALID_ARG, "small_in: bad geometry");
   if (unshuffle > 1 && (H % unshuffle || W % unshuffle))
     return set_error(SRES_ERR_INVALID_ARG, "small_in: unshuffle factor must divide H and W");
-  const long long total = (long long)B * (H + 1) * (W + 1) * 8;
-  long long blocks = (total + 255) / 256;
-  const int cap = small_grid() * 4;
-  if (blocks > cap) blocks = cap;
-  conv3x3_small_in_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in_nchw, w, bias, B, Cs, H, W, transposed,
-                                                                         unshuffle, out_f32, (uint16_t*)out_bf16);
+  const int bands = (H + 1 + kBandRows - 1) / kBandRows;
+  int blocks = B * bands;
+  if (blocks > small_grid() * 2) blocks = small_grid() * 2;
+  const size_t smem = (size_t)Cs * (kBandRows + 2) * (W + 2) * sizeof(float);
+  if (smem > 200 * 1024) return set_error(SRES_ERR_UNSUPPORTED, "small_in: image too wide");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint16_t* o16 = (uint16_t*)out_bf16;
+#define SRES_LAUNCH_SMALL_IN(CS)                                                                                   \
+  do {                                                                                                             \
+    if (smem > 48 * 1024)                                                                                          \
+      cudaFuncSetAttribute(conv3x3_small_in_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    conv3x3_small_in_kernel<CS><<<blocks, 256, smem, st>>>(in_nchw, w, bias, B, H, W, transposed, unshuffle, out_f32, o16); \
+  } while (0)
+  switch (Cs) {
+    case 1: SRES_LAUNCH_SMALL_IN(1); break;
+    case 2: SRES_LAUNCH_SMALL_IN(2); break;
+    case 3: SRES_LAUNCH_SMALL_IN(3); break;
+    default: SRES_LAUNCH_SMALL_IN(4); break;
+  }
+#undef SRES_LAUNCH_SMALL_IN
   SRES_CHECK_LAUNCH("small_in: launch");
   return SRES_OK;
 }
@@ -246,8 +289,25 @@ extern "C" int sres_small_out_wgrad(const float* dout_nchw, const void* u_bf16, 
   const int grid = small_grid();
   if (workspace_bytes < (size_t)grid * 64 * kSwAcc * sizeof(float))
     return set_error(SRES_ERR_INVALID_ARG, "small_out_wgrad: workspace too small");
-  small_out_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dout_nchw, (const uint16_t*)u_bf16, B, Cs, H, W,
-                                                                 (float*)workspace);
+  size_t smem = (size_t)Cs * (kBandRows + 2) * (W + 2) * sizeof(float);
+  const size_t red = (size_t)8 * 64 * kSwAcc * sizeof(float);
+  if (smem < red) smem = red;
+  if (smem > 200 * 1024) return set_error(SRES_ERR_UNSUPPORTED, "small_out_wgrad: image too wide");
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint16_t* u16 = (const uint16_t*)u_bf16;
+  float* partp = (float*)workspace;
+#define SRES_LAUNCH_SMALL_OUT(CS)                                                                               \
+  do {                                                                                                          \
+    cudaFuncSetAttribute(small_out_wgrad_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    small_out_wgrad_kernel<CS><<<grid, 256, smem, st>>>(dout_nchw, u16, B, H, W, partp);                        \
+  } while (0)
+  switch (Cs) {
+    case 1: SRES_LAUNCH_SMALL_OUT(1); break;
+    case 2: SRES_LAUNCH_SMALL_OUT(2); break;
+    case 3: SRES_LAUNCH_SMALL_OUT(3); break;
+    default: SRES_LAUNCH_SMALL_OUT(4); break;
+  }
+#undef SRES_LAUNCH_SMALL_OUT
   SRES_CHECK_LAUNCH("small_out_wgrad: launch");
   small_out_wgrad_reduce_kernel<<<(64 * kSwAcc + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, grid,
                                                                                              Cs, dw, db, accumulate);

@@ -6,6 +6,7 @@ library every entry point raises.
 """
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -90,6 +91,11 @@ class RcanEngine:
         self._packed_version: Dict[Tuple[int, int, int, bool], int] = {}
         self._dirty_token = 0  # bumped by in-place updates torch cannot see (fused Adam)
         self.launches = 0      # kernels of ours enqueued so far (for bench accounting)
+        # CUDA graphs: the whole forward (weight re-pack + ~640 kernels) and the whole backward (~1100
+        # kernels) of a given batch shape are captured once and replayed -- static shapes, static workspace.
+        self.use_graphs = os.environ.get("SRES_CUDA_GRAPHS", "1") != "0"
+        self._graphs: Dict[tuple, dict] = {}
+        self._fwd_generation: Dict[Tuple[int, int, int, bool], int] = {}
 
     # -- description / workspace --------------------------------------------------------------
     def desc(self, B: int, H: int, W: int) -> RcanDesc:
@@ -115,6 +121,7 @@ class RcanEngine:
         return ws
 
     def release_workspaces(self):
+        self._graphs.clear()
         self._ws.clear()
         self._packed_version.clear()
 
@@ -151,6 +158,17 @@ class RcanEngine:
         return seg0 + G * grp + 2
 
     # -- forward / backward ---------------------------------------------------------------------
+    def _launch_forward(self, key, x, out, ws, always_pack=False):
+        B, H, W, training = key
+        st = L.cur_stream()
+        if always_pack:
+            L.check(self.lib.sres_rcan_pack_weights(C.byref(self.desc(B, H, W)), L.ptr(self.flat), L.ptr(ws),
+                                                    int(training), st), "sres_rcan_pack_weights")
+        else:
+            self._ensure_packed(key, ws, st)
+        L.check(self.lib.sres_rcan_forward(C.byref(self.desc(B, H, W)), L.ptr(self.flat), L.ptr(x), L.ptr(out),
+                                           L.ptr(ws), int(training), st), "sres_rcan_forward")
+
     def forward(self, x: torch.Tensor, training: bool) -> torch.Tensor:
         if x.device != self.device:
             raise L.SresError(f"input on {x.device}, model on {self.device}")
@@ -159,16 +177,31 @@ class RcanEngine:
         x = x.detach().contiguous().float()
         B, _, H, W = x.shape
         key = (B, H, W, bool(training))
+        sc = self.scale
         with torch.cuda.device(self.device):
             ws = self.workspace(*key)
-            st = L.cur_stream()
-            self._ensure_packed(key, ws, st)
-            sc = self.scale
-            out = torch.empty(B, self.cout, H * sc, W * sc, device=self.device, dtype=torch.float32)
-            L.check(self.lib.sres_rcan_forward(C.byref(self.desc(B, H, W)), L.ptr(self.flat), L.ptr(x), L.ptr(out),
-                                               L.ptr(ws), int(training), st), "sres_rcan_forward")
+            g = self._graphs.get(("fwd", key))
+            if g is not None:
+                g["x"].copy_(x)
+                g["graph"].replay()
+                out = g["out"].clone()
+            else:
+                out = torch.empty(B, self.cout, H * sc, W * sc, device=self.device, dtype=torch.float32)
+                self._launch_forward(key, x, out, ws)
+                if self.use_graphs:
+                    # first call ran eagerly (lazy driver / attribute set-up happens outside capture); capture for the next ones
+                    xs, outs = x.clone(), torch.empty_like(out)
+                    graph = torch.cuda.CUDAGraph()
+                    torch.cuda.synchronize(self.device)
+                    with torch.cuda.graph(graph):
+                        self._launch_forward(key, xs, outs, ws, always_pack=True)
+                    self._graphs[("fwd", key)] = dict(graph=graph, x=xs, out=outs)
+        self._fwd_generation[key] = self._fwd_generation.get(key, 0) + 1
         self.launches += self.launches_forward(H, W)
         return out
+
+    def forward_generation(self, B, H, W) -> int:
+        return self._fwd_generation.get((B, H, W, True), 0)
 
     def num_segments(self) -> int:
         return self.nlayers + 2
@@ -179,17 +212,39 @@ class RcanEngine:
                 "sres_rcan_segment_params")
         return off.value, cnt.value
 
+    def _launch_backward(self, key, x, dout, accumulate, seg_begin, seg_end):
+        B, H, W, _ = key
+        L.check(self.lib.sres_rcan_backward(C.byref(self.desc(B, H, W)), L.ptr(self.flat), L.ptr(x), L.ptr(dout),
+                                            L.ptr(self.flat_grad), int(accumulate), L.ptr(self._ws[key]),
+                                            seg_begin, seg_end, L.cur_stream()), "sres_rcan_backward")
+
     def backward(self, x: torch.Tensor, dout: torch.Tensor, accumulate: bool, seg_begin: int = 0,
                  seg_end: Optional[int] = None):
-        """Gradients of the flat parameter buffer into self.flat_grad for segments [seg_begin, seg_end)."""
+        """Gradients of the flat parameter buffer into self.flat_grad for segments [seg_begin, seg_end).
+        `x` must be the input of the most recent training-mode forward of this shape (its activations are
+        what the workspace holds)."""
         B, _, H, W = x.shape
         key = (B, H, W, True)
         if key not in self._ws:
             raise L.SresError("backward without a matching training-mode forward")
-        seg_end = self.num_segments() if seg_end is None else seg_end
+        nseg = self.num_segments()
+        seg_end = nseg if seg_end is None else seg_end
+        whole = seg_begin == 0 and seg_end == nseg
         with torch.cuda.device(self.device):
-            L.check(self.lib.sres_rcan_backward(C.byref(self.desc(B, H, W)), L.ptr(self.flat), L.ptr(x), L.ptr(dout),
-                                                L.ptr(self.flat_grad), int(accumulate), L.ptr(self._ws[key]),
-                                                seg_begin, seg_end, L.cur_stream()), "sres_rcan_backward")
-        if seg_begin == 0 and seg_end == self.num_segments():
+            fg = self._graphs.get(("fwd", key))
+            if whole and self.use_graphs and fg is not None:
+                gk = ("bwd", key, bool(accumulate))
+                g = self._graphs.get(gk)
+                if g is None:
+                    douts = dout.clone()
+                    graph = torch.cuda.CUDAGraph()
+                    torch.cuda.synchronize(self.device)
+                    with torch.cuda.graph(graph):
+                        self._launch_backward(key, fg["x"], douts, accumulate, 0, nseg)
+                    g = self._graphs[gk] = dict(graph=graph, dout=douts)
+                g["dout"].copy_(dout)
+                g["graph"].replay()
+            else:
+                self._launch_backward(key, x, dout, accumulate, seg_begin, seg_end)
+        if whole:
             self.launches += self.launches_backward()

@@ -60,6 +60,7 @@ class _RcanFunction(torch.autograd.Function):
         xin = x.detach().contiguous().float()
         out = eng.forward(xin, training=True)
         ctx.module = module
+        ctx.generation = eng.forward_generation(xin.shape[0], xin.shape[2], xin.shape[3])
         ctx.save_for_backward(xin)
         return out
 
@@ -67,6 +68,9 @@ class _RcanFunction(torch.autograd.Function):
     def backward(ctx, dout):
         module = ctx.module
         (xin,) = ctx.saved_tensors
+        if ctx.generation != module.engine.forward_generation(xin.shape[0], xin.shape[2], xin.shape[3]):
+            raise L.SresError("backward through a stale RCAN forward: the activation workspace holds one forward per "
+                              "batch shape -- call backward before the next forward of the same shape")
         module._run_backward(xin, dout.contiguous().float())
         return None, None, None
 
