@@ -19,22 +19,33 @@ struct CaGeom {
 };
 
 // ---- shared: s = sigmoid(W2 relu(W1 m + b1) + b2) for one image -----------------------------
-// sm_m[64] must hold the pooled means.  Fills sm_h[hid], sm_s[64].  All 256 threads call.
+// sm_m[64] must hold the pooled means.  Fills sm_h[hid], sm_z[64], sm_s[64].  All 256 threads call.
+// Each output is one warp-wide dot product (coalesced weight rows + shuffle reduce), 8 warps in parallel:
+// the chain is latency-bound, so it must be short -- it sits between two full-tensor passes.
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 __device__ __forceinline__ void ca_mlp(const float* __restrict__ w1, const float* __restrict__ b1,
                                        const float* __restrict__ w2, const float* __restrict__ b2, int hid,
                                        const float* sm_m, float* sm_h, float* sm_z, float* sm_s) {
-  const int tid = threadIdx.x;
-  if (tid < hid) {
-    float a = b1[tid];
-    for (int c = 0; c < 64; ++c) a = fmaf(w1[tid * 64 + c], sm_m[c], a);
-    sm_h[tid] = fmaxf(a, 0.f);
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const float m0 = sm_m[lane], m1 = sm_m[lane + 32];
+  for (int j = wrp; j < hid; j += kCaThreads / 32) {
+    const float v = warp_sum(fmaf(__ldg(w1 + j * 64 + lane), m0, __ldg(w1 + j * 64 + 32 + lane) * m1));
+    if (lane == 0) sm_h[j] = fmaxf(v + __ldg(b1 + j), 0.f);
   }
   __syncthreads();
-  if (tid < 64) {
-    float a = b2[tid];
-    for (int j = 0; j < hid; ++j) a = fmaf(w2[tid * hid + j], sm_h[j], a);
-    sm_z[tid] = a;
-    sm_s[tid] = 1.f / (1.f + expf(-a));
+  for (int c = wrp; c < 64; c += kCaThreads / 32) {
+    float v = lane < hid ? __ldg(w2 + c * hid + lane) * sm_h[lane] : 0.f;
+    if (lane + 32 < hid) v = fmaf(__ldg(w2 + c * hid + lane + 32), sm_h[lane + 32], v);
+    v = warp_sum(v);
+    if (lane == 0) {
+      const float z = v + __ldg(b2 + c);
+      sm_z[c] = z;
+      sm_s[c] = 1.f / (1.f + expf(-z));
+    }
   }
   __syncthreads();
 }
@@ -63,14 +74,20 @@ ca_pool_kernel(CaGeom g, const uint16_t* __restrict__ t2, float* __restrict__ po
 
 // ---- forward --------------------------------------------------------------------------------
 // x_out = x_in + t2 * s ;  xb_out = bf16(x_out) ; block 0 of each image stores mean and s.
+// Low register count on purpose: all blocks of the grid must be co-resident (one wave), otherwise every
+// wave pays the latency-bound pooled-mean + MLP prologue again.
+
 __global__ void __launch_bounds__(kCaThreads)
 ca_apply_fwd_kernel(CaGeom g, const uint16_t* __restrict__ t2, const float* __restrict__ pool_part,
-                    const float* __restrict__ pool_sum, const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
-                    const float* __restrict__ b2, const float* x_in, float* x_out, uint16_t* __restrict__ xb_out,
-                    float* __restrict__ save_mean, float* __restrict__ save_s) {
+                    const float* __restrict__ pool_sum, const float* __restrict__ w1, const float* __restrict__ b1,
+                    const float* __restrict__ w2, const float* __restrict__ b2, const float* x_in, float* x_out,
+                    uint16_t* __restrict__ xb_out, float* __restrict__ save_mean, float* __restrict__ save_s) {
   __shared__ float sm_red[4][64];
   __shared__ float sm_m[64], sm_h[kCaMaxHidden], sm_z[64], sm_s[64];
   const int b = blockIdx.y, tid = threadIdx.x;
+  const int cg = tid & 7;  // 8-channel slice
+  const int per_blk = (g.RP + g.blocks_per_image - 1) / g.blocks_per_image;
+  const int r0 = blockIdx.x * per_blk + (tid >> 3), r1 = min(g.RP, blockIdx.x * per_blk + per_blk);
   // pooled mean from the conv epilogue partials: tiles covering rows [b*RP, (b+1)*RP)
   if (pool_sum) {
     sm_red[tid >> 6][tid & 63] = (tid < 64) ? pool_sum[b * 64 + tid] : 0.f;
@@ -92,27 +109,27 @@ ca_apply_fwd_kernel(CaGeom g, const uint16_t* __restrict__ t2, const float* __re
     save_mean[b * 64 + tid] = sm_m[tid];
     save_s[b * 64 + tid] = sm_s[tid];
   }
-  const int cg = tid & 7;  // 8-channel slice
   float s8[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s8[j] = sm_s[cg * 8 + j];
-  const int per_blk = (g.RP + g.blocks_per_image - 1) / g.blocks_per_image;
-  const int r0 = blockIdx.x * per_blk, r1 = min(g.RP, r0 + per_blk);
-  for (int r = r0 + (tid >> 3); r < r1; r += kCaThreads / 8) {
-    const size_t q = (size_t)b * g.RP + r;
-    const uint4 tv = *reinterpret_cast<const uint4*>(t2 + q * 64 + cg * 8);
-    const float4 xa = *reinterpret_cast<const float4*>(x_in + q * 64 + cg * 8);
-    const float4 xb = *reinterpret_cast<const float4*>(x_in + q * 64 + cg * 8 + 4);
-    float o[8];
-    o[0] = fmaf(bf16_lo(tv.x), s8[0], xa.x); o[1] = fmaf(bf16_hi(tv.x), s8[1], xa.y);
-    o[2] = fmaf(bf16_lo(tv.y), s8[2], xa.z); o[3] = fmaf(bf16_hi(tv.y), s8[3], xa.w);
-    o[4] = fmaf(bf16_lo(tv.z), s8[4], xb.x); o[5] = fmaf(bf16_hi(tv.z), s8[5], xb.y);
-    o[6] = fmaf(bf16_lo(tv.w), s8[6], xb.z); o[7] = fmaf(bf16_hi(tv.w), s8[7], xb.w);
-    *reinterpret_cast<float4*>(x_out + q * 64 + cg * 8) = make_float4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<float4*>(x_out + q * 64 + cg * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
-    if (xb_out)
-      *reinterpret_cast<uint4*>(xb_out + q * 64 + cg * 8) =
-          make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+#pragma unroll 2
+  for (int r = r0; r < r1; r += kCaThreads / 8) {
+    {
+      const size_t q = (size_t)b * g.RP + r;
+      const uint4 tv = *reinterpret_cast<const uint4*>(t2 + q * 64 + cg * 8);
+      const float4 xa = *reinterpret_cast<const float4*>(x_in + q * 64 + cg * 8);
+      const float4 xb = *reinterpret_cast<const float4*>(x_in + q * 64 + cg * 8 + 4);
+      float o[8];
+      o[0] = fmaf(bf16_lo(tv.x), s8[0], xa.x); o[1] = fmaf(bf16_hi(tv.x), s8[1], xa.y);
+      o[2] = fmaf(bf16_lo(tv.y), s8[2], xa.z); o[3] = fmaf(bf16_hi(tv.y), s8[3], xa.w);
+      o[4] = fmaf(bf16_lo(tv.z), s8[4], xb.x); o[5] = fmaf(bf16_hi(tv.z), s8[5], xb.y);
+      o[6] = fmaf(bf16_lo(tv.w), s8[6], xb.z); o[7] = fmaf(bf16_hi(tv.w), s8[7], xb.w);
+      *reinterpret_cast<float4*>(x_out + q * 64 + cg * 8) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(x_out + q * 64 + cg * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      if (xb_out)
+        *reinterpret_cast<uint4*>(xb_out + q * 64 + cg * 8) =
+            make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    }
   }
 }
 
@@ -153,48 +170,63 @@ ca_bwd_apply_kernel(CaGeom g, const float* __restrict__ grad, const float* __res
                     uint16_t* __restrict__ dt2, float* __restrict__ save_ds) {
   __shared__ float sm_m[64], sm_h[kCaMaxHidden], sm_z[64], sm_s[64], sm_dz[64], sm_dh[kCaMaxHidden], sm_dm[64];
   const int b = blockIdx.y, tid = threadIdx.x;
-  if (tid < 64) sm_m[tid] = save_mean[b * 64 + tid];
+  const int lane = tid & 31, wrp = tid >> 5, cg = tid & 7;
+  const int per_blk = (g.RP + g.blocks_per_image - 1) / g.blocks_per_image;
+  const int r0 = blockIdx.x * per_blk + (tid >> 3), r1 = min(g.RP, blockIdx.x * per_blk + per_blk);
+  float ds = 0.f;
+  if (tid < 64) {
+    sm_m[tid] = save_mean[b * 64 + tid];
+    for (int i = 0; i < g.blocks_per_image; ++i) ds += ds_part[((size_t)b * g.blocks_per_image + i) * 64 + tid];
+    if (blockIdx.x == 0) save_ds[b * 64 + tid] = ds;
+  }
   __syncthreads();
   ca_mlp(w1, b1, w2, b2, g.hid, sm_m, sm_h, sm_z, sm_s);
   if (tid < 64) {
-    float ds = 0.f;
-    for (int i = 0; i < g.blocks_per_image; ++i) ds += ds_part[((size_t)b * g.blocks_per_image + i) * 64 + tid];
-    if (blockIdx.x == 0) save_ds[b * 64 + tid] = ds;
     const float s = sm_s[tid];
     sm_dz[tid] = ds * s * (1.f - s);
   }
   __syncthreads();
-  if (tid < g.hid) {
+  {  // dh[j] = relu'(h[j]) * sum_c w2[c][j] dz[c]: thread (j = tid % 64, quarter = tid / 64) sums 16 c's
+    const int j = tid & 63, qd = tid >> 6;
     float a = 0.f;
-    for (int c = 0; c < 64; ++c) a = fmaf(w2[c * g.hid + tid], sm_dz[c], a);
-    sm_dh[tid] = sm_h[tid] > 0.f ? a : 0.f;
+    if (j < g.hid)
+      for (int c = qd * 16; c < qd * 16 + 16; ++c) a = fmaf(__ldg(w2 + c * g.hid + j), sm_dz[c], a);
+    __shared__ float sm_part[4][64];
+    sm_part[qd][j] = a;
+    __syncthreads();
+    if (tid < g.hid) sm_dh[tid] = sm_h[tid] > 0.f ? (sm_part[0][tid] + sm_part[1][tid] + sm_part[2][tid] + sm_part[3][tid]) : 0.f;
   }
   __syncthreads();
-  if (tid < 64) {
+  {  // dm[c] = sum_j w1[j][c] dh[j] / (H*W): coalesced over c, 4 partial sums over j
+    const int c = tid & 63, qd = tid >> 6;
     float a = 0.f;
-    for (int j = 0; j < g.hid; ++j) a = fmaf(w1[j * 64 + tid], sm_dh[j], a);
-    sm_dm[tid] = a / float(g.H * g.W);
+    for (int j = qd; j < g.hid; j += 4) a = fmaf(__ldg(w1 + j * 64 + c), sm_dh[j], a);
+    __shared__ float sm_part2[4][64];
+    sm_part2[qd][c] = a;
+    __syncthreads();
+    if (tid < 64) sm_dm[tid] = (sm_part2[0][tid] + sm_part2[1][tid] + sm_part2[2][tid] + sm_part2[3][tid]) / float(g.H * g.W);
   }
   __syncthreads();
-  const int cg = tid & 7;
+  (void)lane; (void)wrp;
   float s8[8], m8[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s8[j] = sm_s[cg * 8 + j]; m8[j] = sm_dm[cg * 8 + j]; }
-  const int per_blk = (g.RP + g.blocks_per_image - 1) / g.blocks_per_image;
-  const int r0 = blockIdx.x * per_blk, r1 = min(g.RP, r0 + per_blk);
-  for (int r = r0 + (tid >> 3); r < r1; r += kCaThreads / 8) {
-    const size_t q = (size_t)b * g.RP + r;
-    const int y = r / g.P, x = r - y * g.P;
-    uint4 o = make_uint4(0, 0, 0, 0);
-    if (x != g.W && y != g.H) {
-      const float4 ga = *reinterpret_cast<const float4*>(grad + q * 64 + cg * 8);
-      const float4 gb = *reinterpret_cast<const float4*>(grad + q * 64 + cg * 8 + 4);
-      o.x = pack_bf16x2(fmaf(ga.x, s8[0], m8[0]), fmaf(ga.y, s8[1], m8[1]));
-      o.y = pack_bf16x2(fmaf(ga.z, s8[2], m8[2]), fmaf(ga.w, s8[3], m8[3]));
-      o.z = pack_bf16x2(fmaf(gb.x, s8[4], m8[4]), fmaf(gb.y, s8[5], m8[5]));
-      o.w = pack_bf16x2(fmaf(gb.z, s8[6], m8[6]), fmaf(gb.w, s8[7], m8[7]));
+#pragma unroll 2
+  for (int r = r0; r < r1; r += kCaThreads / 8) {
+    {
+      const size_t q = (size_t)b * g.RP + r;
+      const int y = r / g.P, x = r - y * g.P;
+      uint4 o = make_uint4(0, 0, 0, 0);
+      if (x != g.W && y != g.H) {
+        const float4 ga = *reinterpret_cast<const float4*>(grad + q * 64 + cg * 8);
+        const float4 gb = *reinterpret_cast<const float4*>(grad + q * 64 + cg * 8 + 4);
+        o.x = pack_bf16x2(fmaf(ga.x, s8[0], m8[0]), fmaf(ga.y, s8[1], m8[1]));
+        o.y = pack_bf16x2(fmaf(ga.z, s8[2], m8[2]), fmaf(ga.w, s8[3], m8[3]));
+        o.z = pack_bf16x2(fmaf(gb.x, s8[4], m8[4]), fmaf(gb.y, s8[5], m8[5]));
+        o.w = pack_bf16x2(fmaf(gb.z, s8[6], m8[6]), fmaf(gb.w, s8[7], m8[7]));
+      }
+      *reinterpret_cast<uint4*>(dt2 + q * 64 + cg * 8) = o;
     }
-    *reinterpret_cast<uint4*>(dt2 + q * 64 + cg * 8) = o;
   }
 }
 
@@ -286,7 +318,7 @@ static int ca_geom(CaGeom* g, int B, int H, int W, int hid) {
   g->B = B; g->H = H; g->W = W; g->P = W + 1; g->RP = (H + 1) * (W + 1); g->hid = hid;
   int sms = device_sm_count();
   if (sms <= 0) sms = 148;
-  int bpi = (4 * sms + B - 1) / B;            // ~4 blocks per SM in total
+  int bpi = (4 * sms + B - 1) / B;            // ~4 blocks per SM in total: one resident wave
   const int max_bpi = (g->RP + 31) / 32;      // at least one 32-row sweep each
   if (bpi > max_bpi) bpi = max_bpi;
   if (bpi < 1) bpi = 1;
