@@ -232,17 +232,22 @@ class RcanEngine:
         whole = seg_begin == 0 and seg_end == nseg
         with torch.cuda.device(self.device):
             fg = self._graphs.get(("fwd", key))
-            if whole and self.use_graphs and fg is not None:
-                gk = ("bwd", key, bool(accumulate))
+            if self.use_graphs and fg is not None:
+                # one graph per segment range; all ranges of a shape share the static dout / input buffers
+                dk = ("dout", key)
+                if dk not in self._graphs:
+                    self._graphs[dk] = dict(dout=dout.clone())
+                douts = self._graphs[dk]["dout"]
+                if seg_begin == 0:
+                    douts.copy_(dout)
+                gk = ("bwd", key, bool(accumulate), seg_begin, seg_end)
                 g = self._graphs.get(gk)
                 if g is None:
-                    douts = dout.clone()
                     graph = torch.cuda.CUDAGraph()
                     torch.cuda.synchronize(self.device)
                     with torch.cuda.graph(graph):
-                        self._launch_backward(key, fg["x"], douts, accumulate, 0, nseg)
-                    g = self._graphs[gk] = dict(graph=graph, dout=douts)
-                g["dout"].copy_(dout)
+                        self._launch_backward(key, fg["x"], douts, accumulate, seg_begin, seg_end)
+                    g = self._graphs[gk] = dict(graph=graph)
                 g["graph"].replay()
             else:
                 self._launch_backward(key, x, dout, accumulate, seg_begin, seg_end)

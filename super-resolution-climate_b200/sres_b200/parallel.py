@@ -25,22 +25,32 @@ class SegmentAllReduce:
         self.group = process_group
         self.world = dist.get_world_size(process_group)
         self.average = average
-        self.comm_stream = torch.cuda.Stream(device=engine.device)
+        self.on_gpu = torch.device(engine.device).type == "cuda"
+        self.comm_stream = torch.cuda.Stream(device=engine.device) if self.on_gpu else None
         self.segments = [engine.segment_params(s) for s in range(engine.num_segments())]
 
+    def _reduce(self, engine, off, cnt):
+        bucket = engine.flat_grad[off:off + cnt]
+        dist.all_reduce(bucket, group=self.group)
+        if self.average:
+            bucket.div_(self.world)
+
     def backward(self, engine, xin, dout, accumulate: bool):
+        """Run backward segment by segment; the all-reduce of segment s (NCCL, side stream) overlaps the
+        kernels of segment s+1.  Each segment completes the gradients of one contiguous parameter range."""
         if accumulate:
             raise RuntimeError("data-parallel backward needs fresh gradients (optimizer.zero_grad() each step)")
-        main = torch.cuda.current_stream(engine.device)
+        main = torch.cuda.current_stream(engine.device) if self.on_gpu else None
         for seg, (off, cnt) in enumerate(self.segments):
             engine.backward(xin, dout, accumulate=False, seg_begin=seg, seg_end=seg + 1)
-            ev = torch.cuda.Event()
-            ev.record(main)
-            with torch.cuda.stream(self.comm_stream):
-                self.comm_stream.wait_event(ev)
-                bucket = engine.flat_grad[off:off + cnt]
-                dist.all_reduce(bucket, group=self.group)
-                if self.average:
-                    bucket.div_(self.world)
-        main.wait_stream(self.comm_stream)
+            if self.on_gpu:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(self.comm_stream):
+                    self.comm_stream.wait_event(ev)
+                    self._reduce(engine, off, cnt)
+            else:  # host-side logic only (gloo tests)
+                self._reduce(engine, off, cnt)
+        if self.on_gpu:
+            main.wait_stream(self.comm_stream)
         engine.launches += engine.launches_backward()

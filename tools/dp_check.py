@@ -1,0 +1,42 @@
+"""torchrun --nproc-per-node N tools/dp_check.py : DP-N (B tiles per rank) must equal one GPU on the N*B batch."""
+import os, sys
+import torch, torch.distributed as dist
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, os.path.join(ROOT, "super-resolution-climate_b200"))
+from sres_b200 import nn as snn
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+B, C, S = 4, 2, 12
+torch.manual_seed(7)
+kw = dict(nchannels_in=C, nchannels_out=C, nfeatures=64, nlayers=3, nblocks=2, cbottleneck=2, scale=4, device=dev)
+model = snn.RCAN(**kw)
+dist.broadcast(model.engine.flat, src=0); model.engine.mark_params_changed()
+model.enable_data_parallel()
+g = torch.Generator().manual_seed(11)
+hr_all = torch.randn(world * B, C, S * 4, S * 4, generator=g).to(dev)
+hr = hr_all[rank * B:(rank + 1) * B]
+for it in range(3):       # repeat: graphs for forward, eager segmented backward + NCCL on the side stream
+    for p in model.parameters(): p.grad = None
+    prd = model(snn.bicubic_resize(hr, 0.25).requires_grad_(True))
+    loss = snn.loss(prd, hr, "l2", dist.group.WORLD)
+    loss.backward()
+torch.cuda.synchronize()
+ref = snn.RCAN(**kw)
+ref.engine.flat.copy_(model.engine.flat); ref.engine.mark_params_changed()
+prd_r = ref(snn.bicubic_resize(hr_all, 0.25).requires_grad_(True))
+loss_r = snn.loss(prd_r, hr_all, "l2")
+loss_r.backward()
+torch.cuda.synchronize()
+gd, gr = model.engine.flat_grad, ref.engine.flat_grad
+rel = ((gd - gr).norm() / gr.norm()).item()
+same = torch.tensor([float((gd - gr).abs().max())], device=dev)
+allg = [torch.zeros_like(gd) for _ in range(world)]
+dist.all_gather(allg, gd)
+ident = all(torch.equal(allg[0], a) for a in allg)
+if rank == 0:
+    print(f"RESULT dp{world}: loss {loss.item():.7f} vs single-GPU {loss_r.item():.7f}; grad rel-L2 vs single-GPU = {rel:.3e}; identical across ranks = {ident}")
+    assert abs(loss.item() - loss_r.item()) < 1e-6 and rel < 1e-5 and ident
+dist.destroy_process_group()
