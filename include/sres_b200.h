@@ -86,7 +86,8 @@ typedef struct sres_conv_args {
   int32_t map_mode;        /* SRES_MAP_*                                                        */
   int32_t sub_i, sub_j;    /* sub-pixel of SRES_MAP_SHUFFLE                                     */
   int32_t shuffle_factor;  /* PixelShuffle factor of SRES_MAP_(UN)SHUFFLE; 0 means 2             */
-  int32_t debug_flags;     /* bit0: put (addr>>7)&7 in the UMMA descriptor base_offset field (bring-up only) */
+  int32_t debug_flags;     /* bring-up only: bit1 forces the direct (non-TMA) epilogue              */
+  void* debug_timeline;    /* bring-up only: int64 [grid][16] per-CTA clock stamps, or NULL          */
 } sres_conv_args;
 
 /* Number of 128-position M tiles of a (B,H,W) batch (size of pool_part's leading dim). */

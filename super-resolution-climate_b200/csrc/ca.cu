@@ -84,6 +84,8 @@ ca_apply_fwd_kernel(CaGeom g, const uint16_t* __restrict__ t2, const float* __re
                     uint16_t* __restrict__ xb_out, float* __restrict__ save_mean, float* __restrict__ save_s) {
   __shared__ float sm_red[4][64];
   __shared__ float sm_m[64], sm_h[kCaMaxHidden], sm_z[64], sm_s[64];
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.y, tid = threadIdx.x;
   const int cg = tid & 7;  // 8-channel slice
   const int per_blk = (g.RP + g.blocks_per_image - 1) / g.blocks_per_image;
@@ -138,6 +140,8 @@ __global__ void __launch_bounds__(kCaThreads)
 ca_bwd_reduce_kernel(CaGeom g, const float* __restrict__ grad, const uint16_t* __restrict__ t2,
                      float* __restrict__ ds_part) {
   __shared__ float sm[kCaThreads / 8][64 + 1];
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.y, tid = threadIdx.x, cg = tid & 7;
   const int per_blk = (g.RP + g.blocks_per_image - 1) / g.blocks_per_image;
   const int r0 = blockIdx.x * per_blk, r1 = min(g.RP, r0 + per_blk);
@@ -169,6 +173,8 @@ ca_bwd_apply_kernel(CaGeom g, const float* __restrict__ grad, const float* __res
                     const float* __restrict__ b2, const float* __restrict__ save_mean,
                     uint16_t* __restrict__ dt2, float* __restrict__ save_ds) {
   __shared__ float sm_m[64], sm_h[kCaMaxHidden], sm_z[64], sm_s[64], sm_dz[64], sm_dh[kCaMaxHidden], sm_dm[64];
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.y, tid = threadIdx.x;
   const int lane = tid & 31, wrp = tid >> 5, cg = tid & 7;
   const int per_blk = (g.RP + g.blocks_per_image - 1) / g.blocks_per_image;
@@ -357,9 +363,9 @@ extern "C" int sres_ca_apply_fwd(const void* t2_bf16, const float* pool_part, co
   if (!t2_bf16 || (!pool_part && !pool_sum) || !w1 || !b1 || !w2 || !b2 || !x_in || !x_out || !save_mean || !save_s)
     return set_error(SRES_ERR_INVALID_ARG, "ca_apply_fwd: null pointer");
   dim3 grid(g.blocks_per_image, B);
-  ca_apply_fwd_kernel<<<grid, kCaThreads, 0, (cudaStream_t)stream>>>(
-      g, (const uint16_t*)t2_bf16, pool_part, pool_sum, w1, b1, w2, b2, x_in, x_out, (uint16_t*)xb_out_bf16, save_mean, save_s);
-  SRES_CHECK_LAUNCH("ca_apply_fwd: launch");
+  cudaError_t e = launch_pdl_if(pdl_level() >= 2, ca_apply_fwd_kernel, grid, dim3(kCaThreads), 0, (cudaStream_t)stream, g, (const uint16_t*)t2_bf16,
+                             pool_part, pool_sum, w1, b1, w2, b2, x_in, x_out, (uint16_t*)xb_out_bf16, save_mean, save_s);
+  if (e != cudaSuccess) return set_cuda_error(e, "ca_apply_fwd: launch");
   return SRES_OK;
 }
 
@@ -372,11 +378,12 @@ extern "C" int sres_ca_bwd(const float* grad_f32, const void* t2_bf16, const flo
   if (!grad_f32 || !t2_bf16 || !w1 || !b1 || !w2 || !b2 || !save_mean || !ds_part || !dt2_bf16 || !save_ds)
     return set_error(SRES_ERR_INVALID_ARG, "ca_bwd: null pointer");
   dim3 grid(g.blocks_per_image, B);
-  ca_bwd_reduce_kernel<<<grid, kCaThreads, 0, (cudaStream_t)stream>>>(g, grad_f32, (const uint16_t*)t2_bf16, ds_part);
-  SRES_CHECK_LAUNCH("ca_bwd: reduce launch");
-  ca_bwd_apply_kernel<<<grid, kCaThreads, 0, (cudaStream_t)stream>>>(g, grad_f32, ds_part, w1, b1, w2, b2, save_mean,
-                                                                     (uint16_t*)dt2_bf16, save_ds);
-  SRES_CHECK_LAUNCH("ca_bwd: apply launch");
+  cudaError_t e = launch_pdl_if(pdl_level() >= 2, ca_bwd_reduce_kernel, grid, dim3(kCaThreads), 0, (cudaStream_t)stream, g, grad_f32,
+                             (const uint16_t*)t2_bf16, ds_part);
+  if (e != cudaSuccess) return set_cuda_error(e, "ca_bwd: reduce launch");
+  e = launch_pdl_if(pdl_level() >= 2, ca_bwd_apply_kernel, grid, dim3(kCaThreads), 0, (cudaStream_t)stream, g, grad_f32, (const float*)ds_part, w1, b1,
+                 w2, b2, save_mean, (uint16_t*)dt2_bf16, save_ds);
+  if (e != cudaSuccess) return set_cuda_error(e, "ca_bwd: apply launch");
   return SRES_OK;
 }
 

@@ -1,5 +1,6 @@
 // Library-level entry points, error plumbing, TMA descriptor construction.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "internal.h"
 
@@ -15,6 +16,16 @@ int set_cuda_error(cudaError_t e, const char* where) {
   snprintf(t_err, sizeof(t_err), "%s: %s (%s)", where, cudaGetErrorString(e), cudaGetErrorName(e));
   return SRES_ERR_CUDA;
 }
+
+int pdl_level() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SRES_PDL");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+bool pdl_enabled() { return pdl_level() >= 1; }
 
 int device_sm_count() {
   static thread_local int cached_dev = -1, cached_sms = 0;

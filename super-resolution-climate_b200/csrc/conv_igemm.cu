@@ -51,6 +51,7 @@ struct ConvKParams {
   int tma_epi;          // 1: outputs / addends go through smem slabs + TMA, 0: direct global accesses
   int use_o16, use_msk, use_r32, use_o32;
   int off_s16, off_msk, off_s32, off_tail;  // byte offsets from the aligned smem base
+  long long* timeline;  // bring-up only: per-CTA clock stamps [grid][16]
 };
 
 // 16-value butterfly: after the call lane l (even) holds in v[0] the sum over the 32 lanes of
@@ -141,6 +142,17 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction
   const int lane = threadIdx.x & 31;
+  long long* tl = p.timeline ? p.timeline + (size_t)blockIdx.x * 16 : nullptr;
+#define SRES_STAMP(i)                                   \
+  do {                                                  \
+    if (tl && lane == 0) tl[i] = clock64();             \
+  } while (0)
+  if (tl && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    tl[10] = (long long)gt;
+    tl[0] = clock64();
+  }
   constexpr uint32_t tmem_cols = (kAccStages * N_OUT) < 32 ? 32 : (kAccStages * N_OUT);
 
   if (threadIdx.x == 0) {
@@ -167,6 +179,8 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
+  if (warp == 0) SRES_STAMP(1);
+  pdl_launch_dependents();  // the next kernel may start its prologue as soon as SMs free up
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp runs the loop, one elected lane issues) ==========
@@ -175,6 +189,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_expect_tx(bar_w, kWBytes);
       for (int t = 0; t < 9; ++t) tma_load_2d(smem_w + t * N_OUT * 128, &tmW, bar_w, 0, t * N_OUT);
     }
+    pdl_wait();  // the packed weights are old; the activations come from the previous kernel
     int it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int slot = it % p.nstage;
@@ -197,6 +212,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const uint32_t a_lo0 = sdesc_lo(smem_u32(smem_a), 16);
     const uint32_t row_step = uint32_t(p.P) * 8;  // one image row of the halo window, in 16-byte units
     mbar_wait(bar_w, 0, 2);
+    SRES_STAMP(3);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int slot = it % p.nstage;
@@ -205,6 +221,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t aph = (it / kAccStages) & 1;
       mbar_wait(&bar_tempty[acc], aph ^ 1, 3);
       mbar_wait(&bar_full[slot], ph, 4);
+      if (it == 0) SRES_STAMP(4);
       tc_fence_after();
       const uint32_t a_tile = a_lo0 + uint32_t(slot * stage_bytes) / 16;
       const uint32_t d_tmem = tmem_base + uint32_t(acc * N_OUT);
@@ -224,6 +241,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       __syncwarp();
     }
+    SRES_STAMP(5);
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int ew = warp - 4;        // 0..7
@@ -237,6 +255,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint8_t* s32 = smem + p.off_s32 + ew * 4096;   // 32 rows x 128 B (fp32 half rows, 128B swizzle)
     uint64_t* bin = &bar_in[ew];
     const bool use_in = p.tma_epi && (p.use_msk | p.use_r32);
+    pdl_wait();
     int it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int acc = it % kAccStages;
@@ -256,6 +275,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         __syncwarp();
       }
       mbar_wait(&bar_tfull[acc], aph, 5);
+      if (warp == 4) { if (it == 0) SRES_STAMP(6); SRES_STAMP(7); }
       tc_fence_after();
       if (has_work) {
         const int q = row0 + lane;
@@ -432,11 +452,19 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
       }
     }
+    if (warp == 4) SRES_STAMP(8);
     if (p.tma_epi && lane == 0) bulk_wait_all<0>();
+    if (warp == 4) SRES_STAMP(9);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (tl && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    tl[11] = (long long)gt;
+    tl[12] = clock64();
+  }
   if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
 }
 
@@ -462,6 +490,7 @@ static int launch_conv(const sres_conv_args* a, cudaStream_t stream) {
   p.flags = a->epi_flags; p.map_mode = a->map_mode; p.sub_i = a->sub_i; p.sub_j = a->sub_j; p.sf = sf;
   p.bias = a->bias; p.resid = a->resid_f32; p.resid2 = a->resid2_f32; p.mask = (const uint16_t*)a->mask_bf16;
   p.out_f32 = a->out_f32; p.out_bf16 = (uint16_t*)a->out_bf16; p.pool_part = a->pool_part; p.out_nchw = a->out_nchw;
+  p.timeline = (long long*)a->debug_timeline;
   // TMA-staged epilogue whenever rows map to themselves; scattered (PixelShuffle) and planar stores go direct
   p.tma_epi = (a->map_mode == SRES_MAP_IDENT && a->n_out == 64 && !a->out_nchw && !(a->debug_flags & 2)) ? 1 : 0;
   if (p.tma_epi) {
@@ -502,14 +531,25 @@ static int launch_conv(const sres_conv_args* a, cudaStream_t stream) {
   if (sms <= 0) return set_error(SRES_ERR_NO_DEVICE, "conv: no CUDA device");
   const int grid = p.n_tiles < sms ? p.n_tiles : sms;
   cudaError_t e;
+  static thread_local int attr_dev64 = -1, attr_dev16 = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
   if (a->n_out == 64) {
-    e = cudaFuncSetAttribute(conv3x3_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
-    if (e != cudaSuccess) return set_cuda_error(e, "conv: smem attribute");
-    conv3x3_igemm_kernel<64><<<grid, kConvThreads, smem, stream>>>(tmA, tmW, tmO16, tmMsk, tmR32, tmO32, p);
+    if (attr_dev64 != dev) {
+      e = cudaFuncSetAttribute(conv3x3_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+      if (e != cudaSuccess) return set_cuda_error(e, "conv: smem attribute");
+      attr_dev64 = dev;
+    }
+    e = launch_pdl(conv3x3_igemm_kernel<64>, dim3(grid), dim3(kConvThreads), smem, stream, tmA, tmW, tmO16, tmMsk, tmR32, tmO32, p);
+    if (e != cudaSuccess) return set_cuda_error(e, "conv: launch");
   } else {
-    e = cudaFuncSetAttribute(conv3x3_igemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
-    if (e != cudaSuccess) return set_cuda_error(e, "conv: smem attribute");
-    conv3x3_igemm_kernel<16><<<grid, kConvThreads, smem, stream>>>(tmA, tmW, tmO16, tmMsk, tmR32, tmO32, p);
+    if (attr_dev16 != dev) {
+      e = cudaFuncSetAttribute(conv3x3_igemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+      if (e != cudaSuccess) return set_cuda_error(e, "conv: smem attribute");
+      attr_dev16 = dev;
+    }
+    e = launch_pdl(conv3x3_igemm_kernel<16>, dim3(grid), dim3(kConvThreads), smem, stream, tmA, tmW, tmO16, tmMsk, tmR32, tmO32, p);
+    if (e != cudaSuccess) return set_cuda_error(e, "conv: launch");
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "conv: launch");

@@ -78,9 +78,11 @@ conv3x3_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
+  pdl_launch_dependents();
 
   if (warp == 0) {
     const bool leader = elect_one();
+    pdl_wait();
     int it = 0;
     for (int c = split; c < p.n_chunks; c += nsplit, ++it) {
       const int slot = it % p.nstage;
@@ -133,6 +135,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
     // bias gradient: column sums of the dY tile, read straight from the swizzled smem rows.
     const int wq = warp & 3;
     float acc0 = 0.f, acc1 = 0.f;  // channels 2*lane, 2*lane+1 over rows wq*32 .. wq*32+31
+    pdl_wait();  // the partial buffers this CTA overwrites may still be read by the previous batch's reduce
     int it = 0;
     for (int c = split; c < p.n_chunks; c += nsplit, ++it) {
       const int slot = it % p.nstage;
@@ -206,6 +209,8 @@ struct WgReduceJobs {
 
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ part_bias, int max_split,
                                     const __grid_constant__ WgReduceJobs jobs) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int job = blockIdx.y;
   const WgReduceJob& J = jobs.j[job];
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -306,11 +311,12 @@ extern "C" int sres_conv3x3_wgrad_batch(const sres_wgrad_job* jobs, int njobs, i
   const size_t smem = (size_t)nstage * stage_bytes + 1024 + 2048;
   cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_cuda_error(e, "wgrad: smem attribute");
-  conv3x3_wgrad_kernel<<<grid, 256, smem, stream>>>(maps, tmPart, p);
-  SRES_CHECK_LAUNCH("wgrad: launch");
+  e = launch_pdl(conv3x3_wgrad_kernel, dim3(grid), dim3(256), smem, stream, maps, tmPart, p);
+  if (e != cudaSuccess) return set_cuda_error(e, "wgrad: launch");
   const int total = kWgPartFloats + 64;
-  wgrad_reduce_kernel<<<dim3((total + 255) / 256, njobs), 256, 0, stream>>>(part, p.part_bias, p.max_split, rj);
-  SRES_CHECK_LAUNCH("wgrad: reduce launch");
+  e = launch_pdl(wgrad_reduce_kernel, dim3((total + 255) / 256, njobs), dim3(256), 0, stream, (const float*)part,
+                 (const float*)p.part_bias, p.max_split, rj);
+  if (e != cudaSuccess) return set_cuda_error(e, "wgrad: reduce launch");
   return SRES_OK;
 }
 

@@ -26,6 +26,33 @@ int make_tmap_rows64_f32(CUtensorMap* out, const void* base, uint64_t nrows, uin
 // 64B swizzle: the per-warp epilogue slabs of the conv kernel.
 int make_tmap_rows64_half(CUtensorMap* out, const void* base, uint64_t nrows, uint32_t box_rows);
 
+// Launch with the programmatic-stream-serialization attribute (PDL).  SRES_PDL=0 in the environment turns
+// the attribute off (plain stream order) for A/B measurements.
+bool pdl_enabled();
+int pdl_level();  // SRES_PDL: 0 = off, 1 = tensor-core kernels only (default), 2 = also the element-wise kernels
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl_if(bool on, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 #define SRES_CHECK_LAUNCH(where)                                  \
   do {                                                            \
     cudaError_t e__ = cudaGetLastError();                         \

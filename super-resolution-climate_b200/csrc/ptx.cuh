@@ -29,6 +29,14 @@ __device__ __forceinline__ bool elect_one() {
 __device__ unsigned int g_sres_dev_error = 0;
 
 // ---------------------------------------------------------------------------
+// programmatic dependent launch: the next kernel of the stream may start its prologue (barrier init,
+// TMEM allocation, weight loads) while this one drains; it must pdl_wait() before touching anything a
+// predecessor wrote.  Every kernel launched with the attribute calls pdl_wait() on every exit path.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -37,6 +37,7 @@ class ConvArgs(C.Structure):
         ("map_mode", C.c_int32), ("sub_i", C.c_int32), ("sub_j", C.c_int32),
         ("shuffle_factor", C.c_int32),
         ("debug_flags", C.c_int32),
+        ("debug_timeline", C.c_void_p),
     ]
 
 

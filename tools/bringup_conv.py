@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--mode", default="fwd", choices=["fwd", "dgrad", "relu_pool", "shuffle", "resid"])
     ap.add_argument("--iters", type=int, default=0)
     ap.add_argument("--bf16-only", action="store_true")
+    ap.add_argument("--timeline", action="store_true")
     a = ap.parse_args()
     torch.manual_seed(0)
     torch.backends.cudnn.allow_tf32 = False
@@ -152,6 +153,22 @@ def main():
         ms = st.elapsed_time(en) / a.iters
         fl = 2.0 * B * H * W * 64 * (64 if a.nout == 64 else 16) * 9
         print(f"TIMING {ms*1000:.1f} us/conv  {fl/ms/1e9:.1f} TFLOP/s (useful)")
+    if a.timeline:
+        tl = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+        args.debug_timeline = tl.data_ptr()
+        for _ in range(3):
+            lib.sres_conv3x3_igemm(C.byref(args), L.cur_stream())
+        torch.cuda.synchronize()
+        t = tl.cpu().reshape(148, 16).double()
+        g0 = t[:, 10].min()
+        names = {1: "setup done", 3: "weights landed", 4: "first A tile landed", 6: "first accumulator ready", 5: "last MMA issued",
+                 7: "last accumulator ready", 8: "last store issued", 9: "stores drained", 12: "exit"}
+        print("per-CTA timeline, cycles since CTA entry (min / median / max over CTAs):")
+        for i in (1, 3, 4, 6, 5, 7, 8, 9, 12):
+            d = t[:, i] - t[:, 0]
+            print(f"  {names[i]:26s} {d.min():9.0f} {d.median():9.0f} {d.max():9.0f}")
+        st = t[:, 10] - g0; en = t[:, 11] - g0
+        print(f"globaltimer ns: CTA start min/med/max {st.min():.0f}/{st.median():.0f}/{st.max():.0f}  end {en.min():.0f}/{en.median():.0f}/{en.max():.0f}")
 
 
 if __name__ == "__main__":
