@@ -52,6 +52,16 @@ SRES_API int sres_abi_version(void);
 SRES_API const char* sres_last_error(void);
 /* Number of SMs of the current device (grid sizing); <0 on error. */
 SRES_API int sres_device_sm_count(void);
+/* L2 residency hints (optional; plain CUDA access-policy windows).  sres_l2_set_aside reserves up to
+ * `bytes` of L2 for persisting lines on the current device (process-wide CUDA limit);
+ * sres_l2_persist_window marks [base, base+bytes) as persisting for kernels launched on `stream`
+ * afterwards (bytes == 0 clears it).  After sres_l2_set_aside(bytes > 0) the network executor marks
+ * the fp32 residual trunk (forward) and gradient trunk (backward) persisting by itself.        */
+SRES_API int sres_l2_set_aside(size_t bytes);
+SRES_API int sres_l2_persist_window(const void* base, size_t bytes, void* stream);
+/* Development aid: with SRES_PROFILE=1 in the environment (eager launches only) the network executor brackets
+ * every kernel group with CUDA events; this call aggregates them per category into `buf` and clears them. */
+SRES_API int sres_profile_report(char* buf, size_t nbuf);
 /* Rows of the padded tile layout for a (B,H,W) batch. */
 SRES_API int64_t sres_ptl_rows(int B, int H, int W);
 

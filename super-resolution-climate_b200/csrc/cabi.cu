@@ -125,3 +125,48 @@ extern "C" int sres_abi_version(void) { return 1; }
 extern "C" const char* sres_last_error(void) { return sres::t_err; }
 extern "C" int sres_device_sm_count(void) { return sres::device_sm_count(); }
 extern "C" int64_t sres_ptl_rows(int B, int H, int W) { return (int64_t)B * (H + 1) * (W + 1); }
+
+// ---------------------------------------------------------------------------------------------
+// L2 residency hints: keep the fp32 residual / gradient trunk (read-modify-written by every RCAB)
+// in the persisting part of L2 so that it never round-trips through HBM.
+// ---------------------------------------------------------------------------------------------
+namespace sres {
+static bool g_l2_hint = false;  // set once by sres_l2_set_aside(bytes > 0): the executors then mark the trunks persisting
+bool l2_hint_enabled() { return g_l2_hint; }
+}  // namespace sres
+
+extern "C" int sres_l2_set_aside(size_t bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return sres::set_cuda_error(e, "l2_set_aside: device");
+  int max_bytes = 0;
+  cudaDeviceGetAttribute(&max_bytes, cudaDevAttrMaxPersistingL2CacheSize, dev);
+  if (bytes > (size_t)max_bytes) bytes = (size_t)max_bytes;
+  e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes);
+  if (e != cudaSuccess) return sres::set_cuda_error(e, "l2_set_aside: cudaDeviceSetLimit");
+  sres::g_l2_hint = bytes > 0;
+  return SRES_OK;
+}
+
+extern "C" int sres_l2_persist_window(const void* base, size_t bytes, void* stream) {
+  cudaStreamAttrValue v;
+  memset(&v, 0, sizeof(v));
+  if (base && bytes) {
+    int dev = 0, max_win = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    if (max_win > 0 && bytes > (size_t)max_win) bytes = (size_t)max_win;
+    v.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+    v.accessPolicyWindow.num_bytes = bytes;
+    v.accessPolicyWindow.hitRatio = 1.0f;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  } else {
+    v.accessPolicyWindow.num_bytes = 0;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+  }
+  cudaError_t e = cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &v);
+  if (e != cudaSuccess) return sres::set_cuda_error(e, "l2_persist_window: cudaStreamSetAttribute");
+  return SRES_OK;
+}

@@ -28,6 +28,7 @@ int make_tmap_rows64_half(CUtensorMap* out, const void* base, uint64_t nrows, ui
 
 // Launch with the programmatic-stream-serialization attribute (PDL).  SRES_PDL=0 in the environment turns
 // the attribute off (plain stream order) for A/B measurements.
+bool l2_hint_enabled();  // true after sres_l2_set_aside(bytes > 0)
 bool pdl_enabled();
 int pdl_level();  // SRES_PDL: 0 = off, 1 = tensor-core kernels only (default), 2 = also the element-wise kernels
 template <typename... KArgs, typename... Args>

@@ -10,13 +10,52 @@
 // Precision plan (SURVEY.md section 7 "hard parts"): bf16 only where the sole consumer is a
 // tensor-core operand (conv inputs, weights, incoming gradients); the residual trunk, the gradient
 // trunk, pooled statistics, parameter gradients and all accumulation are fp32.
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 #include "internal.h"
 #include "ptx.cuh"
 
 namespace sres {
 
 constexpr int kConvW = 64 * 64 * 9;  // floats of one 64->64 conv weight
+
+// ---------------------------------------------------------------------------------------------
+// Optional in-situ profiler (SRES_PROFILE=1, eager mode only): CUDA events around every enqueued
+// kernel group, aggregated per category by sres_profile_report().  Development aid; off by default.
+// ---------------------------------------------------------------------------------------------
+struct ProfRec { const char* cat; cudaEvent_t a, b; };
+static std::vector<ProfRec>* t_prof = nullptr;  // process-wide (autograd runs backward on its own thread)
+static std::mutex g_prof_mu;
+static bool prof_on() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SRES_PROFILE"); v = (e && atoi(e) > 0) ? 1 : 0; }
+  return v == 1;
+}
+struct ProfScope {
+  cudaStream_t st; ProfRec r; bool on;
+  ProfScope(const char* cat, void* stream) : st((cudaStream_t)stream), on(prof_on()) {
+    if (!on) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (cs != cudaStreamCaptureStatusNone) { on = false; return; }
+    r.cat = cat;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.b, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!t_prof) t_prof = new std::vector<ProfRec>();
+    t_prof->push_back(r);
+  }
+};
+#define PROF(cat) ProfScope prof_scope__(cat, st)
 
 struct Net {
   sres_rcan_desc d;
@@ -207,6 +246,8 @@ static int conv64(const void* in, const void* wp, const float* bias, int B, int 
                   void* out_bf16, unsigned flags = 0, float* pool = nullptr, const float* resid = nullptr,
                   const float* resid2 = nullptr, const void* mask = nullptr, int map = SRES_MAP_IDENT, int si = 0,
                   int sj = 0, int sf = 2) {
+  PROF(map != SRES_MAP_IDENT ? "conv shuffle/unshuffle" : mask ? "conv dgrad+relu-mask" : (resid && out_f32) ? "conv +fp32 addend (rmw)"
+       : (flags & SRES_EPI_POOL) ? "conv fwd +pool" : (flags & SRES_EPI_RELU) ? "conv fwd +relu" : "conv other");
   sres_conv_args a;
   memset(&a, 0, sizeof(a));
   a.in_bf16 = in; a.wpack_bf16 = wp; a.bias = bias; a.resid_f32 = resid; a.resid2_f32 = resid2; a.mask_bf16 = mask;
@@ -236,7 +277,9 @@ static int forward(const Net& n, const float* P, const float* x, float* out, uin
   float* pool_part = (float*)(ws + n.o_pool_part);
   float* pool_sum = (float*)(ws + n.o_pool_sum);
   int xbi = 0;  // index of the bf16 copy of the current trunk value
-  RC(sres_conv3x3_small_in(x, P + n.head_w, P + n.head_b, B, d.cin, H, W, 0, 0, hf, XB(0), st));
+  const bool l2hint = l2_hint_enabled();
+  if (l2hint) RC(sres_l2_persist_window(xf, (size_t)n.lvRows[0] * 256, st));
+  { PROF("head conv"); RC(sres_conv3x3_small_in(x, P + n.head_w, P + n.head_b, B, d.cin, H, W, 0, 0, hf, XB(0), st)); }
   const float* gin = hf;
   for (int g = 0; g < G; ++g) {
     float* gout = (float*)(ws + n.o_gf[g & 1]);
@@ -255,8 +298,9 @@ static int forward(const Net& n, const float* P, const float* x, float* out, uin
       if (!fused_pool) RC(sres_ca_pool(T2(ti), pool_sum, B, H, W, st));
       float* mean = (float*)(ws + n.o_mean) + (size_t)(training ? ti : 0) * B * 64;
       float* sv = (float*)(ws + n.o_s) + (size_t)(training ? ti : 0) * B * 64;
+      { PROF("ca_apply_fwd");
       RC(sres_ca_apply_fwd(T2(ti), fused_pool ? pool_part : nullptr, fused_pool ? nullptr : pool_sum, w1, b1, w2, b2,
-                           n.hid, r == 0 ? gin : xf, xf, XB(xbi + 1), mean, sv, B, H, W, st));
+                           n.hid, r == 0 ? gin : xf, xf, XB(xbi + 1), mean, sv, B, H, W, st)); }
       ++xbi;
     }
     const float* pg = P + n.off_gt(g);
@@ -264,6 +308,7 @@ static int forward(const Net& n, const float* P, const float* x, float* out, uin
     ++xbi;
     gin = gout;
   }
+  if (l2hint) RC(sres_l2_persist_window(nullptr, 0, st));
   void* resb = ws + n.o_resb;
   RC(conv64(XB(xbi), WF(n.cidx_bt()), P + n.bt_b, B, H, W, st, nullptr, resb, 0, nullptr, hf));
   const void* cur = resb;
@@ -280,7 +325,7 @@ static int forward(const Net& n, const float* P, const float* x, float* out, uin
   a.in_bf16 = cur; a.wpack_bf16 = ws + n.o_wp_tail; a.bias = (const float*)(ws + n.o_bias_tail);
   a.out_nchw = out; a.c_real = d.cout; a.n_out = 16;
   a.B = B; a.H = n.lvH[d.n_up]; a.W = n.lvW[d.n_up];
-  RC(sres_conv3x3_igemm(&a, st));
+  { PROF("tail conv (N=16)"); RC(sres_conv3x3_igemm(&a, st)); }
   return SRES_OK;
 }
 
@@ -299,6 +344,7 @@ struct WgQueue {
   void* st = nullptr;
   int flush() {
     if (n == 0) return SRES_OK;
+    PROF("wgrad batch (+reduce)");
     const int rc = sres_conv3x3_wgrad_batch(jobs, n, B, H, W, ws + net->o_wg_ws, sres_conv_wgrad_workspace_bytes(), st);
     n = 0;
     return rc;
@@ -343,8 +389,10 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
     if (seg == 0) {
       const int Hh = n.lvH[L], Wh = n.lvW[L];
       const void* u_last = L > 0 ? (const void*)(ws + n.o_u[L - 1]) : (const void*)(ws + n.o_resb);
+      { PROF("tail wgrad");
       RC(sres_small_out_wgrad(dout, u_last, B, d.cout, Hh, Wh, Gr + n.tail_w, Gr + n.tail_b, accumulate, ws + n.o_sw_ws,
-                              sres_small_wgrad_workspace_bytes(), st));
+                              sres_small_wgrad_workspace_bytes(), st)); }
+      PROF("tail dgrad + upsampler bwd + body-tail");
       if (L == 0) {
         RC(sres_conv3x3_small_in(dout, P + n.tail_w, nullptr, B, d.cout, Hh, Wh, 1, 0, dres32, dres16, st));
       } else {
@@ -376,6 +424,8 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
     } else if (seg <= G) {
       const int g = G - seg;
       const int xb0 = g * (R + 1);  // XB index of the group's input
+      const bool l2hint = l2_hint_enabled();
+      if (l2hint) RC(sres_l2_persist_window(gb32, (size_t)n.lvRows[0] * 256, st));
       float* Gg = Gr + n.off_gt(g);
       RC(wq.push(XB(xb0 + R), gb16, B, H, W, Gg, Gg + kConvW, 64, 1, 0, accumulate));
       RC(conv64(gb16, WD(n.cidx_gt(g)), nullptr, B, H, W, st, gb32, nullptr));
@@ -392,7 +442,8 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
         void* dt2 = ws + n.o_dt2[ti % 3];
         void* dt1 = ws + n.o_dt1[ti % 3];
         RC(wq.before_write(dt2));
-        RC(sres_ca_bwd(gb32, T2(ti), w1, b1, w2, b2, n.hid, mean, (float*)(ws + n.o_ds_part), dt2, dsv, B, H, W, st));
+        { PROF("ca_bwd (reduce+apply)");
+        RC(sres_ca_bwd(gb32, T2(ti), w1, b1, w2, b2, n.hid, mean, (float*)(ws + n.o_ds_part), dt2, dsv, B, H, W, st)); }
         RC(wq.push(T1(ti), dt2, B, H, W, gr + kConvW + 64, gr + 2 * kConvW + 64, 64, 1, 0, accumulate));
         RC(wq.before_write(dt1));
         RC(conv64(dt2, WD(n.cidx(g, r, 1)), nullptr, B, H, W, st, nullptr, dt1, 0, nullptr, nullptr, nullptr, T1(ti)));
@@ -406,11 +457,14 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
         }
       }
       RC(wq.flush());
+      if (l2hint) RC(sres_l2_persist_window(nullptr, 0, st));
       const long long first = n.off_rcab(g, 0) + 2 * (kConvW + 64);
+      PROF("ca_param_grads");
       RC(sres_ca_param_grads(P + first, Gr + first, n.rcab_sz, R, (const float*)(ws + n.o_mean) + (size_t)g * R * B * 64,
                              (const float*)(ws + n.o_ds) + (size_t)g * R * B * 64, B, n.hid, accumulate, ws + n.o_ca_scr,
                              sres_ca_param_grads_scratch_bytes(R, B), st));
     } else if (seg == G + 1) {
+      PROF("head wgrad");
       RC(sres_small_in_wgrad(ga, dres32, x, B, d.cin, H, W, Gr + n.head_w, Gr + n.head_b, accumulate, ws + n.o_sw_ws,
                              sres_small_wgrad_workspace_bytes(), st));
     }
@@ -478,4 +532,30 @@ extern "C" int sres_rcan_backward(const sres_rcan_desc* d, const float* params, 
   if (seg_begin < 0 || seg_end > d->n_groups + 2 || seg_begin > seg_end)
     return set_error(SRES_ERR_INVALID_ARG, "rcan: bad segment range");
   return backward(n, params, x_nchw, dout_nchw, grads, accumulate, (uint8_t*)workspace, seg_begin, seg_end, stream);
+}
+
+// Aggregate and clear the SRES_PROFILE records of the calling thread (synchronises the device).
+extern "C" int sres_profile_report(char* buf, size_t nbuf) {
+  using namespace sres;
+  if (!buf || nbuf == 0) return set_error(SRES_ERR_INVALID_ARG, "profile_report: no buffer");
+  buf[0] = 0;
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!t_prof || t_prof->empty()) return SRES_OK;
+  std::map<std::string, std::pair<int, double>> agg;
+  double total = 0;
+  for (auto& r : *t_prof) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    agg[r.cat].first += 1; agg[r.cat].second += ms; total += ms;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  t_prof->clear();
+  size_t off = 0;
+  off += snprintf(buf + off, nbuf - off, "total %.3f ms\n", total);
+  for (auto& kv : agg)
+    if (off < nbuf) off += snprintf(buf + off, nbuf - off, "%-40s n=%5d  %8.3f ms  %5.1f%%  avg %7.1f us\n", kv.first.c_str(),
+                                    kv.second.first, kv.second.second, 100.0 * kv.second.second / total,
+                                    1e3 * kv.second.second / kv.second.first);
+  return SRES_OK;
 }
