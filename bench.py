@@ -205,6 +205,23 @@ def run_cuda(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / (float(t.item()) / 1e3)
 
+    # ---- inference (BASELINE config 4, model part): batched forward without gradients, output megapixels/s ------
+    model.eval()
+    with torch.no_grad():
+        for i in range(3):
+            trainer.apply_network(resident[i % nbuf])
+        sync_all()
+        e0.record()
+        for i in range(args.steps):
+            trainer.apply_network(resident[i % nbuf])
+        e1.record()
+        sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    infer_tiles_s = world * B * args.steps / (float(t.item()) / 1e3)
+    model.train()
+
     # ---- roofline of the dominant kernel: the 64->64 tensor-core conv, timed live with CUDA events ---
     import ctypes as C
     rows = B * (TILE + 1) * (TILE + 1)
@@ -262,6 +279,9 @@ def run_cuda(args):
                      "peak_source": pk["src"] + " burst (kernel timed alone)", "us_per_launch": conv_ms * 1e3,
                      "step_tflops_per_gpu": step_tflops, "step_frac_of_sustained": step_tflops / pk["tflops_sustained"]},
         "cpu_baseline": cpu,
+        "inference": {"value": infer_tiles_s * (TILE * SCALE) ** 2 / 1e6, "unit": "output MP/s", "tiles_per_s": infer_tiles_s,
+                      "what": "bicubic down + RCAN-full forward (no grad) on resident 64-tile batches, all GPUs",
+                      "frac_of_tensor_peak": infer_tiles_s / world * flops_per_tile(False) / 1e12 / pk["tflops_sustained"]},
     }
     print(json.dumps(line), flush=True)
     if world > 1:
