@@ -73,6 +73,8 @@ SRES_API int64_t sres_ptl_rows(int B, int H, int W);
 /* ------------------------------------------------------------------------------------------ */
 #define SRES_EPI_RELU 1u       /* v = max(v, 0)                       (network.py:57, nn.ReLU) */
 #define SRES_EPI_POOL 2u       /* emit per-tile channel sums for the CA average pool (network.py:35,45) */
+#define SRES_EPI_DOT 4u        /* mask_bf16 is not a ReLU mask but a second factor: emit per-tile channel sums of
+                                  out * mask into pool_part (the ds = sum(g * t2) reduction of the CALayer backward) */
 
 #define SRES_MAP_IDENT 0       /* output position == input position                              */
 #define SRES_MAP_SHUFFLE 1     /* PixelShuffle(f) store: (b,y,x) -> (b,f*y+sub_i,f*x+sub_j) (blocks.py:65,70) */
@@ -178,6 +180,11 @@ SRES_API int sres_ca_apply_fwd(const void* t2_bf16, const float* pool_part, cons
 SRES_API int sres_ca_bwd(const float* grad_f32, const void* t2_bf16, const float* w1, const float* b1,
                          const float* w2, const float* b2, int hidden, const float* save_mean, float* ds_part,
                          void* dt2_bf16, float* save_ds, int B, int H, int W, void* stream);
+/* same, when ds = sum(g * t2) was already reduced per M tile by the convolution that produced g
+ * (SRES_EPI_DOT): tile_part has the layout of pool_part                                             */
+SRES_API int sres_ca_bwd_apply(const float* grad_f32, const float* tile_part, const float* w1, const float* b1,
+                               const float* w2, const float* b2, int hidden, const float* save_mean, void* dt2_bf16,
+                               float* save_ds, int B, int H, int W, void* stream);
 /* parameter gradients of `nlayers` CALayers whose parameters sit layer_stride floats apart;
  * scratch: sres_ca_param_grads_scratch_bytes(nlayers, B) bytes of device memory                   */
 SRES_API size_t sres_ca_param_grads_scratch_bytes(int nlayers, int B);

@@ -111,26 +111,28 @@ ca_apply_fwd_kernel(CaGeom g, const uint16_t* __restrict__ t2, const float* __re
     save_mean[b * 64 + tid] = sm_m[tid];
     save_s[b * 64 + tid] = sm_s[tid];
   }
+  // A thread owns channels [4cg, 4cg+4) and [32+4cg, 32+4cg+4): every load/store instruction of a warp then
+  // covers whole contiguous 128-byte (fp32) / 64-byte (bf16) row halves -- fully coalesced per instruction.
   float s8[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s8[j] = sm_s[cg * 8 + j];
+  for (int j = 0; j < 4; ++j) { s8[j] = sm_s[cg * 4 + j]; s8[4 + j] = sm_s[32 + cg * 4 + j]; }
 #pragma unroll 2
   for (int r = r0; r < r1; r += kCaThreads / 8) {
-    {
-      const size_t q = (size_t)b * g.RP + r;
-      const uint4 tv = *reinterpret_cast<const uint4*>(t2 + q * 64 + cg * 8);
-      const float4 xa = *reinterpret_cast<const float4*>(x_in + q * 64 + cg * 8);
-      const float4 xb = *reinterpret_cast<const float4*>(x_in + q * 64 + cg * 8 + 4);
-      float o[8];
-      o[0] = fmaf(bf16_lo(tv.x), s8[0], xa.x); o[1] = fmaf(bf16_hi(tv.x), s8[1], xa.y);
-      o[2] = fmaf(bf16_lo(tv.y), s8[2], xa.z); o[3] = fmaf(bf16_hi(tv.y), s8[3], xa.w);
-      o[4] = fmaf(bf16_lo(tv.z), s8[4], xb.x); o[5] = fmaf(bf16_hi(tv.z), s8[5], xb.y);
-      o[6] = fmaf(bf16_lo(tv.w), s8[6], xb.z); o[7] = fmaf(bf16_hi(tv.w), s8[7], xb.w);
-      *reinterpret_cast<float4*>(x_out + q * 64 + cg * 8) = make_float4(o[0], o[1], o[2], o[3]);
-      *reinterpret_cast<float4*>(x_out + q * 64 + cg * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
-      if (xb_out)
-        *reinterpret_cast<uint4*>(xb_out + q * 64 + cg * 8) =
-            make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    const size_t q = (size_t)b * g.RP + r;
+    const uint2 ta = *reinterpret_cast<const uint2*>(t2 + q * 64 + cg * 4);
+    const uint2 tb = *reinterpret_cast<const uint2*>(t2 + q * 64 + 32 + cg * 4);
+    const float4 xa = *reinterpret_cast<const float4*>(x_in + q * 64 + cg * 4);
+    const float4 xb = *reinterpret_cast<const float4*>(x_in + q * 64 + 32 + cg * 4);
+    float o[8];
+    o[0] = fmaf(bf16_lo(ta.x), s8[0], xa.x); o[1] = fmaf(bf16_hi(ta.x), s8[1], xa.y);
+    o[2] = fmaf(bf16_lo(ta.y), s8[2], xa.z); o[3] = fmaf(bf16_hi(ta.y), s8[3], xa.w);
+    o[4] = fmaf(bf16_lo(tb.x), s8[4], xb.x); o[5] = fmaf(bf16_hi(tb.x), s8[5], xb.y);
+    o[6] = fmaf(bf16_lo(tb.y), s8[6], xb.z); o[7] = fmaf(bf16_hi(tb.y), s8[7], xb.w);
+    *reinterpret_cast<float4*>(x_out + q * 64 + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(x_out + q * 64 + 32 + cg * 4) = make_float4(o[4], o[5], o[6], o[7]);
+    if (xb_out) {
+      *reinterpret_cast<uint2*>(xb_out + q * 64 + cg * 4) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+      *reinterpret_cast<uint2*>(xb_out + q * 64 + 32 + cg * 4) = make_uint2(pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
     }
   }
 }
@@ -148,16 +150,17 @@ ca_bwd_reduce_kernel(CaGeom g, const float* __restrict__ grad, const uint16_t* _
   float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int r = r0 + (tid >> 3); r < r1; r += kCaThreads / 8) {
     const size_t q = (size_t)b * g.RP + r;
-    const uint4 tv = *reinterpret_cast<const uint4*>(t2 + q * 64 + cg * 8);
-    const float4 ga = *reinterpret_cast<const float4*>(grad + q * 64 + cg * 8);
-    const float4 gb = *reinterpret_cast<const float4*>(grad + q * 64 + cg * 8 + 4);
-    a[0] = fmaf(ga.x, bf16_lo(tv.x), a[0]); a[1] = fmaf(ga.y, bf16_hi(tv.x), a[1]);
-    a[2] = fmaf(ga.z, bf16_lo(tv.y), a[2]); a[3] = fmaf(ga.w, bf16_hi(tv.y), a[3]);
-    a[4] = fmaf(gb.x, bf16_lo(tv.z), a[4]); a[5] = fmaf(gb.y, bf16_hi(tv.z), a[5]);
-    a[6] = fmaf(gb.z, bf16_lo(tv.w), a[6]); a[7] = fmaf(gb.w, bf16_hi(tv.w), a[7]);
+    const uint2 ta = *reinterpret_cast<const uint2*>(t2 + q * 64 + cg * 4);
+    const uint2 tb = *reinterpret_cast<const uint2*>(t2 + q * 64 + 32 + cg * 4);
+    const float4 ga = *reinterpret_cast<const float4*>(grad + q * 64 + cg * 4);
+    const float4 gb = *reinterpret_cast<const float4*>(grad + q * 64 + 32 + cg * 4);
+    a[0] = fmaf(ga.x, bf16_lo(ta.x), a[0]); a[1] = fmaf(ga.y, bf16_hi(ta.x), a[1]);
+    a[2] = fmaf(ga.z, bf16_lo(ta.y), a[2]); a[3] = fmaf(ga.w, bf16_hi(ta.y), a[3]);
+    a[4] = fmaf(gb.x, bf16_lo(tb.x), a[4]); a[5] = fmaf(gb.y, bf16_hi(tb.x), a[5]);
+    a[6] = fmaf(gb.z, bf16_lo(tb.y), a[6]); a[7] = fmaf(gb.w, bf16_hi(tb.y), a[7]);
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) sm[tid >> 3][cg * 8 + j] = a[j];
+  for (int j = 0; j < 4; ++j) { sm[tid >> 3][cg * 4 + j] = a[j]; sm[tid >> 3][32 + cg * 4 + j] = a[4 + j]; }
   __syncthreads();
   if (tid < 64) {
     float s = 0.f;
@@ -169,7 +172,7 @@ ca_bwd_reduce_kernel(CaGeom g, const float* __restrict__ grad, const uint16_t* _
 // ---- backward, pass 2: dt2 = g*s + dm/(H*W) (bf16), padding rows stay 0 ----------------------
 __global__ void __launch_bounds__(kCaThreads)
 ca_bwd_apply_kernel(CaGeom g, const float* __restrict__ grad, const float* __restrict__ ds_part,
-                    const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                    const float* __restrict__ tile_part, const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                     const float* __restrict__ b2, const float* __restrict__ save_mean,
                     uint16_t* __restrict__ dt2, float* __restrict__ save_ds) {
   __shared__ float sm_m[64], sm_h[kCaMaxHidden], sm_z[64], sm_s[64], sm_dz[64], sm_dh[kCaMaxHidden], sm_dm[64];
@@ -180,9 +183,23 @@ ca_bwd_apply_kernel(CaGeom g, const float* __restrict__ grad, const float* __res
   const int per_blk = (g.RP + g.blocks_per_image - 1) / g.blocks_per_image;
   const int r0 = blockIdx.x * per_blk + (tid >> 3), r1 = min(g.RP, blockIdx.x * per_blk + per_blk);
   float ds = 0.f;
+  __shared__ float sm_dsr[4][64];
+  if (tile_part) {  // ds was reduced per M tile by the producing convolution (SRES_EPI_DOT)
+    const int c = tid & 63, part = tid >> 6;
+    const int t0 = (b * g.RP) / 128, t1 = ((b + 1) * g.RP - 1) / 128;
+    float a = 0.f;
+    for (int t = t0; t <= t1; ++t) {
+      const int seg = b - (t * 128) / g.RP;
+      a += tile_part[(((size_t)t * 2 + seg) * 4 + part) * 64 + c];
+    }
+    sm_dsr[part][c] = a;
+  }
+  __syncthreads();
   if (tid < 64) {
     sm_m[tid] = save_mean[b * 64 + tid];
-    for (int i = 0; i < g.blocks_per_image; ++i) ds += ds_part[((size_t)b * g.blocks_per_image + i) * 64 + tid];
+    if (tile_part) ds = (sm_dsr[0][tid] + sm_dsr[1][tid]) + (sm_dsr[2][tid] + sm_dsr[3][tid]);
+    else
+      for (int i = 0; i < g.blocks_per_image; ++i) ds += ds_part[((size_t)b * g.blocks_per_image + i) * 64 + tid];
     if (blockIdx.x == 0) save_ds[b * 64 + tid] = ds;
   }
   __syncthreads();
@@ -216,23 +233,25 @@ ca_bwd_apply_kernel(CaGeom g, const float* __restrict__ grad, const float* __res
   (void)lane; (void)wrp;
   float s8[8], m8[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s8[j] = sm_s[cg * 8 + j]; m8[j] = sm_dm[cg * 8 + j]; }
+  for (int j = 0; j < 4; ++j) {
+    s8[j] = sm_s[cg * 4 + j]; s8[4 + j] = sm_s[32 + cg * 4 + j];
+    m8[j] = sm_dm[cg * 4 + j]; m8[4 + j] = sm_dm[32 + cg * 4 + j];
+  }
 #pragma unroll 2
   for (int r = r0; r < r1; r += kCaThreads / 8) {
-    {
-      const size_t q = (size_t)b * g.RP + r;
-      const int y = r / g.P, x = r - y * g.P;
-      uint4 o = make_uint4(0, 0, 0, 0);
-      if (x != g.W && y != g.H) {
-        const float4 ga = *reinterpret_cast<const float4*>(grad + q * 64 + cg * 8);
-        const float4 gb = *reinterpret_cast<const float4*>(grad + q * 64 + cg * 8 + 4);
-        o.x = pack_bf16x2(fmaf(ga.x, s8[0], m8[0]), fmaf(ga.y, s8[1], m8[1]));
-        o.y = pack_bf16x2(fmaf(ga.z, s8[2], m8[2]), fmaf(ga.w, s8[3], m8[3]));
-        o.z = pack_bf16x2(fmaf(gb.x, s8[4], m8[4]), fmaf(gb.y, s8[5], m8[5]));
-        o.w = pack_bf16x2(fmaf(gb.z, s8[6], m8[6]), fmaf(gb.w, s8[7], m8[7]));
-      }
-      *reinterpret_cast<uint4*>(dt2 + q * 64 + cg * 8) = o;
+    const size_t q = (size_t)b * g.RP + r;
+    const int y = r / g.P, x = r - y * g.P;
+    uint2 oa = make_uint2(0, 0), ob = make_uint2(0, 0);
+    if (x != g.W && y != g.H) {
+      const float4 ga = *reinterpret_cast<const float4*>(grad + q * 64 + cg * 4);
+      const float4 gb = *reinterpret_cast<const float4*>(grad + q * 64 + 32 + cg * 4);
+      oa.x = pack_bf16x2(fmaf(ga.x, s8[0], m8[0]), fmaf(ga.y, s8[1], m8[1]));
+      oa.y = pack_bf16x2(fmaf(ga.z, s8[2], m8[2]), fmaf(ga.w, s8[3], m8[3]));
+      ob.x = pack_bf16x2(fmaf(gb.x, s8[4], m8[4]), fmaf(gb.y, s8[5], m8[5]));
+      ob.y = pack_bf16x2(fmaf(gb.z, s8[6], m8[6]), fmaf(gb.w, s8[7], m8[7]));
     }
+    *reinterpret_cast<uint2*>(dt2 + q * 64 + cg * 4) = oa;
+    *reinterpret_cast<uint2*>(dt2 + q * 64 + 32 + cg * 4) = ob;
   }
 }
 
@@ -381,9 +400,25 @@ extern "C" int sres_ca_bwd(const float* grad_f32, const void* t2_bf16, const flo
   cudaError_t e = launch_pdl_if(pdl_level() >= 2, ca_bwd_reduce_kernel, grid, dim3(kCaThreads), 0, (cudaStream_t)stream, g, grad_f32,
                              (const uint16_t*)t2_bf16, ds_part);
   if (e != cudaSuccess) return set_cuda_error(e, "ca_bwd: reduce launch");
-  e = launch_pdl_if(pdl_level() >= 2, ca_bwd_apply_kernel, grid, dim3(kCaThreads), 0, (cudaStream_t)stream, g, grad_f32, (const float*)ds_part, w1, b1,
+  e = launch_pdl_if(pdl_level() >= 2, ca_bwd_apply_kernel, grid, dim3(kCaThreads), 0, (cudaStream_t)stream, g, grad_f32, (const float*)ds_part, (const float*)nullptr, w1, b1,
                  w2, b2, save_mean, (uint16_t*)dt2_bf16, save_ds);
   if (e != cudaSuccess) return set_cuda_error(e, "ca_bwd: apply launch");
+  return SRES_OK;
+}
+
+extern "C" int sres_ca_bwd_apply(const float* grad_f32, const float* tile_part, const float* w1, const float* b1,
+                                 const float* w2, const float* b2, int hidden, const float* save_mean, void* dt2_bf16,
+                                 float* save_ds, int B, int H, int W, void* stream) {
+  CaGeom g;
+  int rc = ca_geom(&g, B, H, W, hidden);
+  if (rc) return rc;
+  if (g.RP < 128) return set_error(SRES_ERR_UNSUPPORTED, "ca_bwd_apply: per-tile partials need (H+1)*(W+1) >= 128");
+  if (!grad_f32 || !tile_part || !w1 || !b1 || !w2 || !b2 || !save_mean || !dt2_bf16 || !save_ds)
+    return set_error(SRES_ERR_INVALID_ARG, "ca_bwd_apply: null pointer");
+  dim3 grid(g.blocks_per_image, B);
+  cudaError_t e = launch_pdl_if(pdl_level() >= 2, ca_bwd_apply_kernel, grid, dim3(kCaThreads), 0, (cudaStream_t)stream, g, grad_f32,
+                                (const float*)nullptr, tile_part, w1, b1, w2, b2, save_mean, (uint16_t*)dt2_bf16, save_ds);
+  if (e != cudaSuccess) return set_cuda_error(e, "ca_bwd_apply: launch");
   return SRES_OK;
 }
 

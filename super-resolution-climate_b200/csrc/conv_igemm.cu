@@ -326,7 +326,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
             }
-            if (p.use_msk) {
+            if (p.use_msk && !(p.flags & SRES_EPI_DOT)) {
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
                 const uint4 mk = *reinterpret_cast<const uint4*>(rmk + (((ch * 2 + j) ^ sw3) << 4));
@@ -341,6 +341,21 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             if (pad) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            }
+            if (p.flags & SRES_EPI_DOT) {
+              // per-image channel sums of v * other (the channel-attention backward reduction, fused here)
+              float t[16];
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint4 mk = *reinterpret_cast<const uint4*>(rmk + (((ch * 2 + j) ^ sw3) << 4));
+                const uint32_t w4[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  t[8 * j + 2 * e] = v[8 * j + 2 * e] * bf16_lo(w4[e]);
+                  t[8 * j + 2 * e + 1] = v[8 * j + 2 * e + 1] * bf16_hi(w4[e]);
+                }
+              }
+              pool_partials(t, seg, lane, p.pool_part + ((long long)tile * 2 * 4 + wq) * 64 + c0);
             }
             if (p.use_o32) {
 #pragma unroll
@@ -478,7 +493,10 @@ static int launch_conv(const sres_conv_args* a, cudaStream_t stream) {
   const int sf = a->shuffle_factor > 0 ? a->shuffle_factor : 2;
   if (a->map_mode == SRES_MAP_UNSHUFFLE && (a->H % sf || a->W % sf))
     return set_error(SRES_ERR_INVALID_ARG, "conv: unshuffle factor must divide H and W");
-  if ((a->epi_flags & SRES_EPI_POOL) && !a->pool_part) return set_error(SRES_ERR_INVALID_ARG, "conv: pool_part missing");
+  if ((a->epi_flags & (SRES_EPI_POOL | SRES_EPI_DOT)) && !a->pool_part) return set_error(SRES_ERR_INVALID_ARG, "conv: pool_part missing");
+  if ((a->epi_flags & SRES_EPI_DOT) && ((a->epi_flags & SRES_EPI_POOL) || !a->mask_bf16 || a->map_mode != SRES_MAP_IDENT || a->n_out != 64 ||
+                                         a->out_nchw || (a->debug_flags & 2)))
+    return set_error(SRES_ERR_INVALID_ARG, "conv: SRES_EPI_DOT needs mask_bf16 (the other factor), identity mapping, 64 outputs and no SRES_EPI_POOL");
 
   ConvKParams p{};
   p.B = a->B; p.H = a->H; p.W = a->W; p.P = a->W + 1; p.R = a->H + 1;

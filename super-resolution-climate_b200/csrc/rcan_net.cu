@@ -246,7 +246,7 @@ static int conv64(const void* in, const void* wp, const float* bias, int B, int 
                   void* out_bf16, unsigned flags = 0, float* pool = nullptr, const float* resid = nullptr,
                   const float* resid2 = nullptr, const void* mask = nullptr, int map = SRES_MAP_IDENT, int si = 0,
                   int sj = 0, int sf = 2) {
-  PROF(map != SRES_MAP_IDENT ? "conv shuffle/unshuffle" : mask ? "conv dgrad+relu-mask" : (resid && out_f32) ? "conv +fp32 addend (rmw)"
+  PROF(map != SRES_MAP_IDENT ? "conv shuffle/unshuffle" : (flags & SRES_EPI_DOT) ? "conv dgrad +fp32 rmw +ds-dot" : mask ? "conv dgrad+relu-mask" : (resid && out_f32) ? "conv +fp32 addend (rmw)"
        : (flags & SRES_EPI_POOL) ? "conv fwd +pool" : (flags & SRES_EPI_RELU) ? "conv fwd +relu" : "conv other");
   sres_conv_args a;
   memset(&a, 0, sizeof(a));
@@ -384,6 +384,7 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
   float* dres32 = (float*)(ws + n.o_dres32);
   void* dres16 = ws + n.o_dres16;
   const int xb_last = G * (R + 1);  // bf16 copy of the last group's output = body-tail conv input
+  const bool fused_dot = (H + 1) * (W + 1) >= 128;  // per-tile two-segment partials need an image >= one M tile
 
   for (int seg = seg_begin; seg < seg_end; ++seg) {
     if (seg == 0) {
@@ -428,7 +429,10 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
       if (l2hint) RC(sres_l2_persist_window(gb32, (size_t)n.lvRows[0] * 256, st));
       float* Gg = Gr + n.off_gt(g);
       RC(wq.push(XB(xb0 + R), gb16, B, H, W, Gg, Gg + kConvW, 64, 1, 0, accumulate));
-      RC(conv64(gb16, WD(n.cidx_gt(g)), nullptr, B, H, W, st, gb32, nullptr));
+      // the convolution that produces the gradient of RCAB r's output also reduces ds = sum(g * t2_r) per tile
+      float* dot_part = (float*)(ws + n.o_pool_part);
+      RC(conv64(gb16, WD(n.cidx_gt(g)), nullptr, B, H, W, st, gb32, nullptr, fused_dot ? SRES_EPI_DOT : 0,
+                fused_dot ? dot_part : nullptr, nullptr, nullptr, fused_dot ? T2(g * R + R - 1) : nullptr));
       for (int r = R - 1; r >= 0; --r) {
         const int ti = g * R + r;
         const float* pr = P + n.off_rcab(g, r);
@@ -442,14 +446,16 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
         void* dt2 = ws + n.o_dt2[ti % 3];
         void* dt1 = ws + n.o_dt1[ti % 3];
         RC(wq.before_write(dt2));
-        { PROF("ca_bwd (reduce+apply)");
-        RC(sres_ca_bwd(gb32, T2(ti), w1, b1, w2, b2, n.hid, mean, (float*)(ws + n.o_ds_part), dt2, dsv, B, H, W, st)); }
+        { PROF("ca_bwd");
+        if (fused_dot) RC(sres_ca_bwd_apply(gb32, dot_part, w1, b1, w2, b2, n.hid, mean, dt2, dsv, B, H, W, st));
+        else RC(sres_ca_bwd(gb32, T2(ti), w1, b1, w2, b2, n.hid, mean, (float*)(ws + n.o_ds_part), dt2, dsv, B, H, W, st)); }
         RC(wq.push(T1(ti), dt2, B, H, W, gr + kConvW + 64, gr + 2 * kConvW + 64, 64, 1, 0, accumulate));
         RC(wq.before_write(dt1));
         RC(conv64(dt2, WD(n.cidx(g, r, 1)), nullptr, B, H, W, st, nullptr, dt1, 0, nullptr, nullptr, nullptr, T1(ti)));
         RC(wq.push(XB(xb0 + r), dt1, B, H, W, gr, gr + kConvW, 64, 1, 0, accumulate));
         if (r > 0) {
-          RC(conv64(dt1, WD(n.cidx(g, r, 0)), nullptr, B, H, W, st, gb32, nullptr, 0, nullptr, gb32));
+          RC(conv64(dt1, WD(n.cidx(g, r, 0)), nullptr, B, H, W, st, gb32, nullptr, fused_dot ? SRES_EPI_DOT : 0,
+                    fused_dot ? dot_part : nullptr, gb32, nullptr, fused_dot ? T2(ti - 1) : nullptr));
         } else {
           // grad wrt the group input = body path (gb32 + conv1 dgrad) + group skip (ga)
           RC(wq.before_write(gb16));

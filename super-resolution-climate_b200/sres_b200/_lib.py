@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "..", "lib", "libsres_b200.so")
 SRES_OK = 0
 EPI_RELU = 1
 EPI_POOL = 2
+EPI_DOT = 4
 MAP_IDENT, MAP_SHUFFLE, MAP_UNSHUFFLE = 0, 1, 2
 
 

@@ -164,7 +164,7 @@ class RcanEngine:
         seg0_batches = sum(-(-f * f // 4) for f in self.stages) + 1      # per upsampler stage + body-tail conv
         seg0 = 2 + 1 + ups_dgrad + 1 + 2 * seg0_batches                   # tail wgrad(2), tail dgrad, dgrads, bt dgrad
         grp_batches = -(-(1 + 2 * R) // 4)
-        grp = 1 + R * (2 + 1 + 1) + 2 + 2 * grp_batches                   # gt dgrad, per RCAB ca_bwd(2)+2 dgrads, ca params(2)
+        grp = 1 + R * (1 + 1 + 1) + 2 + 2 * grp_batches                   # gt dgrad, per RCAB ca_bwd + 2 dgrads, ca params(2)
         return seg0 + G * grp + 2
 
     # -- forward / backward ---------------------------------------------------------------------

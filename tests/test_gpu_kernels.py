@@ -84,6 +84,24 @@ def test_conv_dgrad_mask_residuals(env, B, H, W):
     run_conv(lib, conv_args(in_bf16=dyp, wpack_bf16=wp, resid_f32=acc, resid2_f32=to_ptl(r2.to(dev), torch.float32), out_f32=acc,
                             B=B, H=H, W=W, n_out=64))
     assert rel_l2(from_ptl(acc, B, H, W).cpu(), ref_res) < 2e-3 and pads_are_zero(acc, B, H, W)
+    if (H + 1) * (W + 1) >= 128:
+        # fused channel-attention backward reduction: per-tile sums of out * other (SRES_EPI_DOT)
+        nt = lib.sres_conv_mtiles(B, H, W)
+        part = torch.full((nt, 2, 4, 64), float("nan"), device=dev)
+        out32 = torch.zeros(dyp.shape[0], 64, device=dev)
+        run_conv(lib, conv_args(in_bf16=dyp, wpack_bf16=wp, mask_bf16=to_ptl(t1.to(dev), torch.bfloat16), out_f32=out32,
+                                pool_part=part, B=B, H=H, W=W, n_out=64, epi_flags=L.EPI_DOT))
+        assert rel_l2(from_ptl(out32, B, H, W).cpu(), dx) < 2e-3          # the mask operand must NOT gate the output
+        RP = (H + 1) * (W + 1)
+        sums = torch.zeros(B, 64)
+        pc = part.cpu()
+        assert torch.isfinite(pc).all()
+        for t in range(nt):
+            b0 = (t * 128) // RP
+            for seg in range(2):
+                if b0 + seg < B:
+                    sums[b0 + seg] += pc[t, seg].sum(0)
+        assert rel_l2(sums, (dx * t1).sum((2, 3))) < 2e-3
 
 
 @pytest.mark.parametrize("f", [2, 3])
