@@ -262,6 +262,14 @@ def run_cuda(args):
         cpu = {"value": tps, "unit": "tiles/s", "cores": threads, "kind": "port",
                "sample": "3 timed steps of batch 2 of the same RCAN-full x4 train step (oracle/rcan_oracle.py, fp32 PyTorch CPU)"}
 
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of the same kernel/shape
+    traffic = None
+    try:
+        m = json.load(open(os.path.join(ROOT, "profiles", "r01_v3_conv_ncu_metrics.json")))
+        conv = {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Gbyte": 1e9}
+        traffic = sum(float(m[k]["value"].replace(",", "")) * conv[m[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    except Exception:
+        pass
     step_tflops = value / world * flops_per_tile(True) / 1e12
     line = {
         "metric": METRIC, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -275,7 +283,9 @@ def run_cuda(args):
         "gpu_launches": per_step_launches * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv3x3_igemm_kernel<64> (64->64 conv, B=64, 48x48)", "achieved": achieved,
-                     "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_burst"], "traffic": None,
+                     "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_burst"], "traffic": traffic,
+                     "traffic_note": "DRAM bytes per launch (ncu --set full, profiles/r01_v3_conv_ncu_metrics.json); algorithmic 39.3 MB "
+                                     "(19.7 in + 19.7 out): the input is read once, the output is still in L2 when the kernel ends",
                      "peak_source": pk["src"] + " burst (kernel timed alone)", "us_per_launch": conv_ms * 1e3,
                      "step_tflops_per_gpu": step_tflops, "step_frac_of_sustained": step_tflops / pk["tflops_sustained"]},
         "cpu_baseline": cpu,
