@@ -253,9 +253,14 @@ SRES_API int sres_rcan_forward(const sres_rcan_desc* d, const float* params, con
  * the all-reduce of that range while the next segment runs.                                     */
 SRES_API int sres_rcan_num_segments(const sres_rcan_desc* d);
 SRES_API int sres_rcan_segment_params(const sres_rcan_desc* d, int seg, int64_t* offset, int64_t* count);
+/* async_ctx (optional, from sres_async_create; NULL = everything on `stream`): a side stream + events owned by the
+ * caller on which the weight-gradient batches run beside the input-gradient chain; every segment joins it back
+ * into `stream` before returning, so stream order (and CUDA-graph capture of `stream`) still covers all work.   */
+SRES_API int sres_async_create(void** ctx);
+SRES_API int sres_async_destroy(void* ctx);
 SRES_API int sres_rcan_backward(const sres_rcan_desc* d, const float* params, const float* x_nchw,
                                 const float* dout_nchw, float* grads, int accumulate, void* workspace, int seg_begin,
-                                int seg_end, void* stream);
+                                int seg_end, void* async_ctx, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Tile extraction / normalisation / stitching (index-exact data movement around the model)   */

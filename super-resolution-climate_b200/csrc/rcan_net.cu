@@ -336,16 +336,58 @@ static int forward(const Net& n, const float* P, const float* x, float* out, uin
 // Deferred weight-gradient jobs: up to 4 of the same geometry go out as one batched launch.  A job only
 // reads saved activations and a bf16 output-gradient buffer; the queue is flushed before any kernel that
 // overwrites such a buffer is enqueued, when it is full, and at the end of every backward segment.
+// Optional second stream for the weight-gradient batches: they depend only on saved activations and on
+// output-gradient buffers already produced, so they can run beside the input-gradient chain and fill the
+// SM time that chain leaves idle (kernel tails, element-wise kernels that leave the tensor cores free).
+struct AsyncCtx {
+  static constexpr int kEvents = 8;
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork[kEvents], done[kEvents];
+  const void* bufs[kEvents][SRES_WGRAD_MAX_JOBS];  // dy buffers a side batch still reads
+  bool live[kEvents];
+  int next = 0;
+};
+
 struct WgQueue {
   sres_wgrad_job jobs[SRES_WGRAD_MAX_JOBS];
   int n = 0, B = 0, H = 0, W = 0;
   const Net* net = nullptr;
   uint8_t* ws = nullptr;
   void* st = nullptr;
+  AsyncCtx* ax = nullptr;
+  int wait_slot(int i) {  // main stream waits for side batch i
+    if (ax && ax->live[i]) {
+      cudaError_t e = cudaStreamWaitEvent((cudaStream_t)st, ax->done[i], 0);
+      if (e != cudaSuccess) return set_cuda_error(e, "backward: join side stream");
+      ax->live[i] = false;
+    }
+    return SRES_OK;
+  }
+  int join_all() {
+    if (ax)
+      for (int i = 0; i < AsyncCtx::kEvents; ++i) RC(wait_slot(i));
+    return SRES_OK;
+  }
   int flush() {
     if (n == 0) return SRES_OK;
     PROF("wgrad batch (+reduce)");
-    const int rc = sres_conv3x3_wgrad_batch(jobs, n, B, H, W, ws + net->o_wg_ws, sres_conv_wgrad_workspace_bytes(), st);
+    int rc;
+    if (ax) {
+      const int i = ax->next;
+      ax->next = (i + 1) % AsyncCtx::kEvents;
+      RC(wait_slot(i));
+      cudaError_t e = cudaEventRecord(ax->fork[i], (cudaStream_t)st);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(ax->side, ax->fork[i], 0);
+      if (e != cudaSuccess) return set_cuda_error(e, "backward: fork side stream");
+      rc = sres_conv3x3_wgrad_batch(jobs, n, B, H, W, ws + net->o_wg_ws, sres_conv_wgrad_workspace_bytes(), ax->side);
+      if (rc) return rc;
+      e = cudaEventRecord(ax->done[i], ax->side);
+      if (e != cudaSuccess) return set_cuda_error(e, "backward: side event");
+      for (int k = 0; k < SRES_WGRAD_MAX_JOBS; ++k) ax->bufs[i][k] = k < n ? jobs[k].dy_bf16 : nullptr;
+      ax->live[i] = true;
+    } else {
+      rc = sres_conv3x3_wgrad_batch(jobs, n, B, H, W, ws + net->o_wg_ws, sres_conv_wgrad_workspace_bytes(), st);
+    }
     n = 0;
     return rc;
   }
@@ -362,13 +404,18 @@ struct WgQueue {
   // call before enqueuing a kernel that writes `buf`
   int before_write(const void* buf) {
     for (int i = 0; i < n; ++i)
-      if (jobs[i].dy_bf16 == buf) return flush();
+      if (jobs[i].dy_bf16 == buf) { RC(flush()); break; }
+    if (ax)
+      for (int i = 0; i < AsyncCtx::kEvents; ++i)
+        if (ax->live[i])
+          for (int k = 0; k < SRES_WGRAD_MAX_JOBS; ++k)
+            if (ax->bufs[i][k] == buf) { RC(wait_slot(i)); break; }
     return SRES_OK;
   }
 };
 
 static int backward(const Net& n, const float* P, const float* x, const float* dout, float* Gr, int accumulate,
-                    uint8_t* ws, int seg_begin, int seg_end, void* st) {
+                    uint8_t* ws, int seg_begin, int seg_end, AsyncCtx* ax, void* st) {
   const sres_rcan_desc& d = n.d;
   const int B = d.B, H = d.H, W = d.W, G = d.n_groups, R = d.n_blocks, L = d.n_up;
   const size_t bf = (size_t)n.lvRows[0] * 128;
@@ -380,7 +427,8 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
   float* gb32 = (float*)(ws + n.o_gb32);
   void* gb16 = ws + n.o_gb16;
   WgQueue wq;
-  wq.net = &n; wq.ws = ws; wq.st = st;
+  wq.net = &n; wq.ws = ws; wq.st = st; wq.ax = ax;
+  if (ax) for (int i = 0; i < AsyncCtx::kEvents; ++i) ax->live[i] = false;
   float* dres32 = (float*)(ws + n.o_dres32);
   void* dres16 = ws + n.o_dres16;
   const int xb_last = G * (R + 1);  // bf16 copy of the last group's output = body-tail conv input
@@ -422,6 +470,7 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
       RC(wq.before_write(gb16));
       RC(conv64(dres16, WD(n.cidx_bt()), nullptr, B, H, W, st, ga, gb16));
       RC(wq.flush());
+      RC(wq.join_all());
     } else if (seg <= G) {
       const int g = G - seg;
       const int xb0 = g * (R + 1);  // XB index of the group's input
@@ -463,6 +512,7 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
         }
       }
       RC(wq.flush());
+      RC(wq.join_all());
       if (l2hint) RC(sres_l2_persist_window(nullptr, 0, st));
       const long long first = n.off_rcab(g, 0) + 2 * (kConvW + 64);
       PROF("ca_param_grads");
@@ -528,16 +578,40 @@ extern "C" int sres_rcan_forward(const sres_rcan_desc* d, const float* params, c
   return forward(n, params, x_nchw, out_nchw, (uint8_t*)workspace, training, stream);
 }
 
+extern "C" int sres_async_create(void** out) {
+  if (!out) return set_error(SRES_ERR_INVALID_ARG, "async_create: null output");
+  AsyncCtx* a = new AsyncCtx();
+  cudaError_t e = cudaStreamCreateWithFlags(&a->side, cudaStreamNonBlocking);
+  for (int i = 0; i < AsyncCtx::kEvents && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&a->fork[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->done[i], cudaEventDisableTiming);
+    a->live[i] = false;
+  }
+  if (e != cudaSuccess) { delete a; return set_cuda_error(e, "async_create"); }
+  *out = a;
+  return SRES_OK;
+}
+
+extern "C" int sres_async_destroy(void* ctx) {
+  AsyncCtx* a = (AsyncCtx*)ctx;
+  if (!a) return SRES_OK;
+  for (int i = 0; i < AsyncCtx::kEvents; ++i) { cudaEventDestroy(a->fork[i]); cudaEventDestroy(a->done[i]); }
+  cudaStreamDestroy(a->side);
+  delete a;
+  return SRES_OK;
+}
+
 extern "C" int sres_rcan_backward(const sres_rcan_desc* d, const float* params, const float* x_nchw,
                                   const float* dout_nchw, float* grads, int accumulate, void* workspace, int seg_begin,
-                                  int seg_end, void* stream) {
+                                  int seg_end, void* async_ctx, void* stream) {
   Net n;
   int rc = build_net(&n, d, 1);
   if (rc) return rc;
   if (!params || !x_nchw || !dout_nchw || !grads || !workspace) return set_error(SRES_ERR_INVALID_ARG, "rcan: null pointer");
   if (seg_begin < 0 || seg_end > d->n_groups + 2 || seg_begin > seg_end)
     return set_error(SRES_ERR_INVALID_ARG, "rcan: bad segment range");
-  return backward(n, params, x_nchw, dout_nchw, grads, accumulate, (uint8_t*)workspace, seg_begin, seg_end, stream);
+  return backward(n, params, x_nchw, dout_nchw, grads, accumulate, (uint8_t*)workspace, seg_begin, seg_end, (AsyncCtx*)async_ctx,
+                  stream);
 }
 
 // Aggregate and clear the SRES_PROFILE records of the calling thread (synchronises the device).

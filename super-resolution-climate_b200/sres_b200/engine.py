@@ -95,6 +95,11 @@ class RcanEngine:
         # kernels) of a given batch shape are captured once and replayed -- static shapes, static workspace.
         self.use_graphs = os.environ.get("SRES_CUDA_GRAPHS", "1") != "0"
         self._l2_set = False
+        # weight-gradient batches on a side stream (SRES_SIDE_STREAM=0 keeps everything on one stream)
+        self._async = C.c_void_p(None)
+        if os.environ.get("SRES_SIDE_STREAM", "1") != "0":
+            with torch.cuda.device(device):
+                L.check(self.lib.sres_async_create(C.byref(self._async)), "sres_async_create")
         self._graphs: Dict[tuple, dict] = {}
         self._fwd_generation: Dict[Tuple[int, int, int, bool], int] = {}
 
@@ -226,7 +231,7 @@ class RcanEngine:
         B, H, W, _ = key
         L.check(self.lib.sres_rcan_backward(C.byref(self.desc(B, H, W)), L.ptr(self.flat), L.ptr(x), L.ptr(dout),
                                             L.ptr(self.flat_grad), int(accumulate), L.ptr(self._ws[key]),
-                                            seg_begin, seg_end, L.cur_stream()), "sres_rcan_backward")
+                                            seg_begin, seg_end, self._async, L.cur_stream()), "sres_rcan_backward")
 
     def backward(self, x: torch.Tensor, dout: torch.Tensor, accumulate: bool, seg_begin: int = 0,
                  seg_end: Optional[int] = None):
