@@ -104,6 +104,8 @@ typedef struct sres_conv_args {
 
 /* Number of 128-position M tiles of a (B,H,W) batch (size of pool_part's leading dim). */
 SRES_API int sres_conv_mtiles(int B, int H, int W);
+/* 1 when a (H,W) image fits the tensor-core kernel's shared-memory halo window for n_out outputs, else 0 */
+SRES_API int sres_conv_supported(int H, int W, int n_out);
 SRES_API int sres_conv3x3_igemm(const sres_conv_args* args, void* stream);
 
 /* Repack fp32 OIHW 3x3 weights (the checkpoint layout, state_dict of nn.Conv2d) to the bf16
@@ -152,6 +154,10 @@ SRES_API int sres_conv3x3_wgrad(const void* x_bf16, const void* dy_bf16, int B, 
 SRES_API int sres_conv3x3_small_in(const float* in_nchw, const float* w, const float* bias, int B, int Cs, int H,
                                    int W, int transposed, int unshuffle, float* out_f32, void* out_bf16,
                                    void* stream);
+/* tail conv forward 64 -> Cs on CUDA cores (bf16 PTL in, planar fp32 out): the path for images too wide for the
+ * tensor-core kernel's halo window; w (Cs,64,3,3)                                                       */
+SRES_API int sres_conv3x3_small_out(const void* u_bf16, const float* w, const float* bias, int B, int Cs, int H, int W,
+                                    float* out_nchw, void* stream);
 SRES_API size_t sres_small_wgrad_workspace_bytes(void);
 /* head conv weight/bias gradient; the output gradient is g1 (+ g2 when not NULL), fp32 PTL      */
 SRES_API int sres_small_in_wgrad(const float* g1_f32, const float* g2_f32, const float* in_nchw, int B, int Cs,

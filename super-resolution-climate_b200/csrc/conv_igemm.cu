@@ -518,10 +518,15 @@ static int launch_conv(const sres_conv_args* a, cudaStream_t stream) {
   const int wbytes = 9 * a->n_out * 128;
   const int smem_max = 232448;  // 227 KB
   const int tail_bytes = 1024;
-  const int slab_bytes = (p.use_o16 ? 16384 : 0) + (p.use_msk ? 16384 : 0) + ((p.use_r32 | p.use_o32) ? 32768 : 0);
+  int slab_bytes = (p.use_o16 ? 16384 : 0) + (p.use_msk ? 16384 : 0) + ((p.use_r32 | p.use_o32) ? 32768 : 0);
   const int rows = 128 + 2 * (p.P + 1);
   p.stage_rows = (rows + kBoxRows - 1) / kBoxRows * kBoxRows;
   int ns = (smem_max - 1024 - wbytes - tail_bytes - slab_bytes) / (p.stage_rows * 128);
+  if (ns < 1 && p.tma_epi && !(a->epi_flags & SRES_EPI_DOT)) {  // wide image: give the slab space to the halo window
+    p.tma_epi = p.use_o16 = p.use_msk = p.use_r32 = p.use_o32 = 0;
+    slab_bytes = 0;
+    ns = (smem_max - 1024 - wbytes - tail_bytes) / (p.stage_rows * 128);
+  }
   if (ns > kMaxStages) ns = kMaxStages;
   if (ns < 1) return set_error(SRES_ERR_UNSUPPORTED, "conv: image too wide for the flat halo window");
   p.nstage = ns;
@@ -579,6 +584,15 @@ static int launch_conv(const sres_conv_args* a, cudaStream_t stream) {
 extern "C" int sres_conv_mtiles(int B, int H, int W) {
   long long npos = (long long)B * (H + 1) * (W + 1);
   return (int)((npos + 127) / 128);
+}
+
+extern "C" int sres_conv_supported(int H, int W, int n_out) {
+  (void)H;
+  const int wbytes = 9 * n_out * 128;
+  const int rows = 128 + 2 * (W + 2);
+  const int stage_rows = (rows + sres::kBoxRows - 1) / sres::kBoxRows * sres::kBoxRows;
+  // one ring slot next to the weights (the epilogue falls back to direct stores when its slabs do not fit)
+  return (232448 - 1024 - wbytes - 1024) / (stage_rows * 128) >= 1 ? 1 : 0;
 }
 
 extern "C" int sres_conv3x3_igemm(const sres_conv_args* args, void* stream) {

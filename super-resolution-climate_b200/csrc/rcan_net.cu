@@ -325,7 +325,13 @@ static int forward(const Net& n, const float* P, const float* x, float* out, uin
   a.in_bf16 = cur; a.wpack_bf16 = ws + n.o_wp_tail; a.bias = (const float*)(ws + n.o_bias_tail);
   a.out_nchw = out; a.c_real = d.cout; a.n_out = 16;
   a.B = B; a.H = n.lvH[d.n_up]; a.W = n.lvW[d.n_up];
-  { PROF("tail conv (N=16)"); RC(sres_conv3x3_igemm(&a, st)); }
+  if (sres_conv_supported(a.H, a.W, 16)) {
+    PROF("tail conv (N=16)");
+    RC(sres_conv3x3_igemm(&a, st));
+  } else {  // very wide images (x8 of 96x96): HBM-bound CUDA-core kernel, no halo window in shared memory
+    PROF("tail conv (CUDA cores)");
+    RC(sres_conv3x3_small_out(cur, P + n.tail_w, P + n.tail_b, B, d.cout, a.H, a.W, out, st));
+  }
   return SRES_OK;
 }
 

@@ -222,6 +222,53 @@ __global__ void small_out_wgrad_reduce_kernel(const float* __restrict__ part, in
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// tail conv forward on CUDA cores: 64-feature bf16 PTL -> planar fp32 (B,Cs,H,W).  Used when the image is too
+// wide for the tensor-core kernel's flat halo window (W > ~700: the x8 up-scaling of 96x96 tiles); the op is
+// HBM-bound either way (it reads 128 B per pixel and writes 4*Cs).  One warp per output pixel: lanes split
+// the 64 input features (2 each), 9 taps, shuffle reduction.
+// ---------------------------------------------------------------------------------------------
+template <int CS>
+__global__ void __launch_bounds__(256)
+small_out_fwd_kernel(const uint16_t* __restrict__ u, const float* __restrict__ w, const float* __restrict__ bias, int B,
+                     int H, int W, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  float wr[CS][9][2];
+#pragma unroll
+  for (int c = 0; c < CS; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      wr[c][t][0] = w[(c * 64 + 2 * lane) * 9 + t];
+      wr[c][t][1] = w[(c * 64 + 2 * lane + 1) * 9 + t];
+    }
+  const int P = W + 1;
+  const long long RP = (long long)(H + 1) * P;
+  const long long npix = (long long)B * H * W;
+  for (long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); pix < npix; pix += (long long)gridDim.x * 8) {
+    const int x = int(pix % W), y = int((pix / W) % H), b = int(pix / ((long long)W * H));
+    const long long q = b * RP + (long long)y * P + x;
+    float acc[CS];
+#pragma unroll
+    for (int c = 0; c < CS; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const long long qq = q + (t / 3 - 1) * P + (t % 3 - 1);   // padding rows are zero; only the buffer ends need a guard
+      if (qq < 0 || qq >= (long long)B * RP) continue;
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(u + qq * 64 + 2 * lane);
+      const float v0 = bf16_lo(v), v1 = bf16_hi(v);
+#pragma unroll
+      for (int c = 0; c < CS; ++c) acc[c] = fmaf(wr[c][t][0], v0, fmaf(wr[c][t][1], v1, acc[c]));
+    }
+#pragma unroll
+    for (int c = 0; c < CS; ++c) {
+      float a = acc[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) out[(((long long)b * CS + c) * H + y) * W + x] = a + (bias ? bias[c] : 0.f);
+    }
+  }
+}
+
 static int small_grid() {
   int sms = device_sm_count();
   if (sms <= 0) sms = 148;
@@ -312,5 +359,23 @@ extern "C" int sres_small_out_wgrad(const float* dout_nchw, const void* u_bf16, 
   small_out_wgrad_reduce_kernel<<<(64 * kSwAcc + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, grid,
                                                                                              Cs, dw, db, accumulate);
   SRES_CHECK_LAUNCH("small_out_wgrad: reduce launch");
+  return SRES_OK;
+}
+
+extern "C" int sres_conv3x3_small_out(const void* u_bf16, const float* w, const float* bias, int B, int Cs, int H, int W,
+                                      float* out_nchw, void* stream) {
+  if (!u_bf16 || !w || !out_nchw) return set_error(SRES_ERR_INVALID_ARG, "small_out: null pointer");
+  if (Cs < 1 || Cs > kMaxSmallC) return set_error(SRES_ERR_UNSUPPORTED, "small_out: 1..4 image channels supported");
+  if (B <= 0 || H <= 0 || W <= 0) return set_error(SRES_ERR_INVALID_ARG, "small_out: bad geometry");
+  const int grid = small_grid() * 4;
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint16_t* u16 = (const uint16_t*)u_bf16;
+  switch (Cs) {
+    case 1: small_out_fwd_kernel<1><<<grid, 256, 0, st>>>(u16, w, bias, B, H, W, out_nchw); break;
+    case 2: small_out_fwd_kernel<2><<<grid, 256, 0, st>>>(u16, w, bias, B, H, W, out_nchw); break;
+    case 3: small_out_fwd_kernel<3><<<grid, 256, 0, st>>>(u16, w, bias, B, H, W, out_nchw); break;
+    default: small_out_fwd_kernel<4><<<grid, 256, 0, st>>>(u16, w, bias, B, H, W, out_nchw); break;
+  }
+  SRES_CHECK_LAUNCH("small_out: launch");
   return SRES_OK;
 }

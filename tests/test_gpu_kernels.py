@@ -217,6 +217,22 @@ def test_head_and_tail_convs(env):
         assert rel_l2(dbt.cpu(), dout.sum((0, 2, 3))) < 1e-4
 
 
+def test_tail_conv_cuda_core_path_and_wide_images(env):
+    """64 -> Cs tail conv on CUDA cores (the path for images wider than the tensor-core halo window) and the
+    support predicate that selects it."""
+    L, lib, dev = env
+    assert lib.sres_conv_supported(192, 192, 16) == 1 and lib.sres_conv_supported(768, 768, 16) == 0
+    assert lib.sres_conv_supported(48, 48, 64) == 1 and lib.sres_conv_supported(384, 384, 64) == 1
+    for Cs, B, H, W in [(2, 2, 20, 24), (4, 1, 9, 130)]:
+        u = bf16_round(torch.randn(B, 64, H, W))
+        wt, bt = torch.randn(Cs, 64, 3, 3) * 0.05, torch.randn(Cs)
+        out = torch.full((B, Cs, H, W), float("nan"), device=dev)
+        L.check(lib.sres_conv3x3_small_out(ptr(to_ptl(u.to(dev), torch.bfloat16)), ptr(wt.to(dev)), ptr(bt.to(dev)), B, Cs, H, W,
+                                           ptr(out), L.cur_stream()), "small_out")
+        torch.cuda.synchronize()
+        assert rel_l2(out.cpu(), F.conv2d(u, wt, bt, padding=1)) < 1e-5
+
+
 @pytest.mark.parametrize("B,H,W,red", [(3, 20, 24, 2), (2, 48, 48, 16), (4, 7, 9, 4)])
 def test_channel_attention_forward_backward(env, B, H, W, red):
     """CALayer + RCAB residual against autograd of the oracle's ca_layer (network.py:44-47, 61-64)."""

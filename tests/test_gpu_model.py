@@ -85,6 +85,26 @@ def test_train_step_matches_oracle_and_golden(name, dev, golden_dir):
     assert rel_l2(prd2.cpu(), prd_o) < TOL
 
 
+def test_x8_wide_tiles_forward_and_backward_run(dev):
+    """BASELINE config 5 geometry (x8, 4 channels, 96x96 LR -> 768x768 HR) at batch 1: wider than the tensor-core
+    halo window at the last level, so the tail conv takes the CUDA-core path.  Checked against the oracle."""
+    from sres_b200 import nn as snn
+    cfg = O.model_cfg(nlayers=1, nblocks=1, downscale_factors=[2, 2, 2])
+    sd = O.make_state_dict(cfg, 4, 4)
+    hr = synth_hr(1, 4, 768, smooth=True)
+    loss_o, prd_o, grads_o = O.loss_and_grads(hr, sd, cfg, "l2")
+    model = _build(cfg, 4, dev)
+    model.load_state_dict(sd)
+    hr_d = hr.to(dev)
+    prd = model(snn.bicubic_resize(hr_d, 1.0 / 8).requires_grad_(True))
+    loss = snn.loss(prd, hr_d, "l2")
+    loss.backward()
+    assert prd.shape == (1, 4, 768, 768) and rel_l2(prd.detach().cpu(), prd_o) < TOL
+    num = sum((p.grad.cpu() - grads_o[k]).double().pow(2).sum().item() for k, p in model.named_parameters())
+    den = sum(g.double().pow(2).sum().item() for g in grads_o.values())
+    assert (num / den) ** 0.5 < TOL and abs(loss.item() - loss_o) < TOL * abs(loss_o)
+
+
 def test_gradient_accumulation_and_stock_adam(dev):
     """Two backward passes without zero_grad accumulate (autograd semantics); torch.optim.Adam works on the
     parameter views and its in-place update is picked up by the next forward (weights are re-packed)."""
