@@ -117,7 +117,47 @@ __device__ __forceinline__ void pool_partials(const float (&v)[16], int seg, int
   }
 }
 
-template <int N_OUT>
+// Column sums in the accumulator-fragment layout: every thread holds 8 partial sums (column 8k + 2(lane%4) + e
+// at index 2k + e) over its own rows; three exchange stages over lane bits 4,3,2 leave ONE column total per
+// lane: column 16*bit4 + 8*bit3 + 2*(lane%4) + bit2.  7 shuffles per 32 columns.
+__device__ __forceinline__ float frag_colsum(float (&w)[8], int lane) {
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? w[i] : w[i + 4];
+      const float keep = up ? w[i + 4] : w[i];
+      w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? w[i] : w[i + 2];
+      const float keep = up ? w[i + 2] : w[i];
+      w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = lane & 4;
+    const float send = up ? w[0] : w[1];
+    const float keep = up ? w[1] : w[0];
+    w[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  return w[0];
+}
+
+// PAIR = true: launched as clusters of two CTAs that run every UMMA together (cta_group::2, M = 256): tile
+// 2k goes to the pair's rank 0, tile 2k+1 to rank 1, and each CTA keeps only HALF of the packed weights
+// (output features [32*rank, 32*rank+32) of every tap) -- a third less B-operand traffic out of shared
+// memory, which is what bounds this kernel, and 36 KB more room for the halo ring.
+// FL >= 0: an instance specialised at compile time for one epilogue flavour of the TMA-staged path (bit set below);
+// the RCAB loop's four convolutions each get one, which keeps the epilogue's code and instruction count small --
+// it shares the SM's issue ports and instruction cache with the single MMA-issuing thread.  FL = -1 is the generic
+// kernel (runtime flags, all mappings).  kFlFrag selects the fragment-layout epilogue for the column reductions.
+constexpr int kFlO16 = 1, kFlO32 = 2, kFlR32 = 4, kFlMsk = 8, kFlRelu = 16, kFlPool = 32, kFlDot = 64, kFlFrag = 128;
+template <int N_OUT, bool PAIR, int FL>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                      const __grid_constant__ CUtensorMap tmO16, const __grid_constant__ CUtensorMap tmMsk,
@@ -125,8 +165,12 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                      const ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-B aligned carve-up (128B swizzle atoms are 1024 B).
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int kWBytes = 9 * N_OUT * 128;
+  // offset arithmetic (not an integer round trip) keeps the pointer in the shared address space: LDS/STS, not generic LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int kWRows = PAIR ? N_OUT / 2 : N_OUT;  // weight rows (output features) per tap held by this CTA
+  constexpr int kWBytes = 9 * kWRows * 128;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool lead_cta = rank == 0;
   uint8_t* smem_w = smem;
   uint8_t* smem_a = smem + kWBytes;
   const int stage_bytes = p.stage_rows * 128;
@@ -152,6 +196,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
     tl[10] = (long long)gt;
     tl[0] = clock64();
+    tl[13] = tl[14] = tl[15] = 0;
   }
   constexpr uint32_t tmem_cols = (kAccStages * N_OUT) < 32 ? 32 : (kAccStages * N_OUT);
 
@@ -165,18 +210,24 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     mbar_init(bar_w, 1);
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&bar_tfull[i], 1);
-      mbar_init(&bar_tempty[i], 8);  // one arrive per epilogue warp
+      mbar_init(&bar_tempty[i], PAIR ? 16 : 8);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     for (int i = 0; i < 8; ++i) mbar_init(&bar_in[i], 1);
     mbar_fence_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_holder, tmem_cols);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc2(tmem_holder, tmem_cols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_holder, tmem_cols);
+      tmem_relinquish();
+    }
   }
   if (threadIdx.x < N_OUT) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
   if (warp == 0) SRES_STAMP(1);
@@ -186,27 +237,39 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ===================== TMA producer (whole warp runs the loop, one elected lane issues) ==========
     const bool leader = elect_one();
     if (leader) {
-      mbar_expect_tx(bar_w, kWBytes);
-      for (int t = 0; t < 9; ++t) tma_load_2d(smem_w + t * N_OUT * 128, &tmW, bar_w, 0, t * N_OUT);
+      if constexpr (PAIR) {
+        const uint32_t lbar_w = mapa_u32(smem_u32(bar_w), 0);
+        if (lead_cta) mbar_expect_tx(bar_w, 2 * kWBytes);
+        for (int t = 0; t < 9; ++t) tma_load_2d_pair(smem_w + t * kWRows * 128, &tmW, lbar_w, 0, t * N_OUT + int(rank) * kWRows);
+      } else {
+        mbar_expect_tx(bar_w, kWBytes);
+        for (int t = 0; t < 9; ++t) tma_load_2d(smem_w + t * N_OUT * 128, &tmW, bar_w, 0, t * N_OUT);
+      }
     }
     pdl_wait();  // the packed weights are old; the activations come from the previous kernel
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; (PAIR ? (tile & ~1) : tile) < p.n_tiles; tile += gridDim.x, ++it) {
       const int slot = it % p.nstage;
       const uint32_t ph = (it / p.nstage) & 1;
       mbar_wait(&bar_empty[slot], ph ^ 1, 1);
       const int row0 = tile * 128 - (p.P + 1);
       uint8_t* dst = smem_a + slot * stage_bytes;
       if (leader) {
-        mbar_expect_tx(&bar_full[slot], stage_bytes);
-        for (int r = 0; r < p.stage_rows; r += kBoxRows) tma_load_2d(dst + r * 128, &tmA, &bar_full[slot], 0, row0 + r);
+        if constexpr (PAIR) {  // both CTAs' bytes complete on the leader CTA's barrier
+          const uint32_t lbar = mapa_u32(smem_u32(&bar_full[slot]), 0);
+          if (lead_cta) mbar_expect_tx(&bar_full[slot], 2 * stage_bytes);
+          for (int r = 0; r < p.stage_rows; r += kBoxRows) tma_load_2d_pair(dst + r * 128, &tmA, lbar, 0, row0 + r);
+        } else {
+          mbar_expect_tx(&bar_full[slot], stage_bytes);
+          for (int r = 0; r < p.stage_rows; r += kBoxRows) tma_load_2d(dst + r * 128, &tmA, &bar_full[slot], 0, row0 + r);
+        }
       }
       __syncwarp();
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && lead_cta) {
     // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) ==========
     const bool leader = elect_one();
-    constexpr uint32_t idesc = make_idesc_bf16(128, N_OUT, 0, 0);
+    constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, N_OUT, 0, 0);
     constexpr uint32_t dhi = sdesc_hi_sw128(1024);
     const uint32_t w_lo = sdesc_lo(smem_u32(smem_w), 16);
     const uint32_t a_lo0 = sdesc_lo(smem_u32(smem_a), 16);
@@ -214,13 +277,17 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     mbar_wait(bar_w, 0, 2);
     SRES_STAMP(3);
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; (PAIR ? (tile & ~1) : tile) < p.n_tiles; tile += gridDim.x, ++it) {
       const int slot = it % p.nstage;
       const uint32_t ph = (it / p.nstage) & 1;
       const int acc = it % kAccStages;
       const uint32_t aph = (it / kAccStages) & 1;
+      long long w0 = 0, w1 = 0;
+      if (tl) w0 = clock64();
       mbar_wait(&bar_tempty[acc], aph ^ 1, 3);
+      if (tl) w1 = clock64();
       mbar_wait(&bar_full[slot], ph, 4);
+      if (tl && lane == 0) { tl[14] += w1 - w0; tl[15] += clock64() - w1; }   // waiting for the epilogue / for TMA
       if (it == 0) SRES_STAMP(4);
       tc_fence_after();
       const uint32_t a_tile = a_lo0 + uint32_t(slot * stage_bytes) / 16;
@@ -229,15 +296,25 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
           const uint32_t a_tap = a_tile + uint32_t(t / 3) * row_step + uint32_t(t % 3) * 8;
-          const uint32_t b_tap = w_lo + uint32_t(t * N_OUT * 8);
+          const uint32_t b_tap = w_lo + uint32_t(t * kWRows * 8);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            if (t == 0 && k == 0) umma_bf16_lohi<false>(d_tmem, a_tap, dhi, b_tap, dhi, idesc);
-            else umma_bf16_lohi<true>(d_tmem, a_tap + k * 2, dhi, b_tap + k * 2, dhi, idesc);
+            if constexpr (PAIR) {
+              if (t == 0 && k == 0) umma2_bf16_lohi<false>(d_tmem, a_tap, dhi, b_tap, dhi, idesc);
+              else umma2_bf16_lohi<true>(d_tmem, a_tap + k * 2, dhi, b_tap + k * 2, dhi, idesc);
+            } else {
+              if (t == 0 && k == 0) umma_bf16_lohi<false>(d_tmem, a_tap, dhi, b_tap, dhi, idesc);
+              else umma_bf16_lohi<true>(d_tmem, a_tap + k * 2, dhi, b_tap + k * 2, dhi, idesc);
+            }
           }
         }
-        umma_commit(&bar_empty[slot]);  // smem slot free once these MMAs retire
-        umma_commit(&bar_tfull[acc]);   // accumulator ready
+        if constexpr (PAIR) {
+          umma_commit2(&bar_empty[slot]);  // both CTAs' ring slots / accumulators
+          umma_commit2(&bar_tfull[acc]);
+        } else {
+          umma_commit(&bar_empty[slot]);  // smem slot free once these MMAs retire
+          umma_commit(&bar_tfull[acc]);   // accumulator ready
+        }
       }
       __syncwarp();
     }
@@ -254,27 +331,50 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint8_t* smk = smem + p.off_msk + ew * 2048;
     uint8_t* s32 = smem + p.off_s32 + ew * 4096;   // 32 rows x 128 B (fp32 half rows, 128B swizzle)
     uint64_t* bin = &bar_in[ew];
-    const bool use_in = p.tma_epi && (p.use_msk | p.use_r32);
+    constexpr bool kSpec = FL >= 0;
+    constexpr bool FRAG = kSpec && (FL & kFlFrag);
+    const bool f_tma = kSpec ? true : bool(p.tma_epi);
+    const bool f_o16 = kSpec ? bool(FL & kFlO16) : bool(p.use_o16);
+    const bool f_o32 = kSpec ? bool(FL & kFlO32) : bool(p.use_o32);
+    const bool f_r32 = kSpec ? bool(FL & kFlR32) : bool(p.use_r32);
+    const bool f_msk = kSpec ? bool(FL & kFlMsk) : bool(p.use_msk);
+    const bool f_relu = kSpec ? bool(FL & kFlRelu) : bool(p.flags & SRES_EPI_RELU);
+    const bool f_pool = kSpec ? bool(FL & kFlPool) : bool(p.flags & SRES_EPI_POOL);
+    const bool f_dot = kSpec ? bool(FL & kFlDot) : bool(p.flags & SRES_EPI_DOT);
+    const float* f_res2 = kSpec ? nullptr : p.resid2;
+    const bool use_in = f_tma && (f_msk | f_r32);
+    // per-tile column reductions (pooled sums / channel-attention dot products) run in the fragment layout
+    const int fm = lane & 3, frq = lane >> 2;            // fragment column pair / row within an 8-row group
+    const int fcol = ((lane >> 4) & 1) * 16 + ((lane >> 3) & 1) * 8 + 2 * fm + ((lane >> 2) & 1);  // column after frag_colsum
+    float bias8[8];
+    if constexpr (FRAG) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bias8[i] = s_bias[(half * 32 + 8 * (i >> 1) + 2 * fm + (i & 1)) % N_OUT];
+    }
     pdl_wait();
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; (PAIR ? (tile & ~1) : tile) < p.n_tiles; tile += gridDim.x, ++it) {
       const int acc = it % kAccStages;
       const uint32_t aph = (it / kAccStages) & 1;
       const int row0 = tile * 128 + wq * 32;
-      if (p.tma_epi) {
+      const bool tile_ok = !PAIR || tile < p.n_tiles;  // an odd tile count leaves rank 1's last tile empty
+      if (f_tma) {
         // the slab must have been read out by the previous tile's TMA stores; then prefetch this tile's
         // fp32 addend / mask while the tensor core is still working on it
         if (lane == 0) {
           bulk_wait_read<0>();
           if (use_in) {
-            mbar_expect_tx(bin, (p.use_msk ? 2048u : 0u) + (p.use_r32 ? 4096u : 0u));
-            if (p.use_msk) tma_load_2d(smk, &tmMsk, bin, half * 32, row0);
-            if (p.use_r32) tma_load_2d(s32, &tmR32, bin, half * 32, row0);
+            mbar_expect_tx(bin, (f_msk ? 2048u : 0u) + (f_r32 ? 4096u : 0u));
+            if (f_msk) tma_load_2d(smk, &tmMsk, bin, half * 32, row0);
+            if (f_r32) tma_load_2d(s32, &tmR32, bin, half * 32, row0);
           }
         }
         __syncwarp();
       }
+      long long e0 = 0;
+      if (tl && warp == 4) e0 = clock64();
       mbar_wait(&bar_tfull[acc], aph, 5);
+      if (tl && warp == 4 && lane == 0) tl[13] += clock64() - e0;   // epilogue idle, waiting for the tensor core
       if (warp == 4) { if (it == 0) SRES_STAMP(6); SRES_STAMP(7); }
       tc_fence_after();
       if (has_work) {
@@ -287,6 +387,65 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const bool pad = (x == p.W) || (y == p.H) || !inrange;
         const int seg = (b != (tile * 128) / RP) ? 1 : 0;
         const uint32_t trow = tmem_base + (uint32_t(wq * 32) << 16) + uint32_t(acc * N_OUT + half * 32);
+        if constexpr (FRAG) {
+          // ---------------- fragment-layout epilogue: thread = rows frq + 8j (j < 4) x column pairs 8k + 2fm ----------------
+          uint32_t fa[16], fb[16];
+          tmem_ld_frag16(trow, fa);
+          tmem_ld_frag16(trow + (16u << 16), fb);
+          const unsigned padmask = __ballot_sync(0xffffffffu, pad);
+          const unsigned seg1 = __ballot_sync(0xffffffffu, seg == 1);
+          const bool mixed = seg1 != 0u && seg1 != 0xffffffffu;   // the warp's rows straddle two images
+          tmem_ld_wait();
+          if (use_in) mbar_wait(bin, it & 1, 6);
+          const int sw3 = (frq >> 1) & 3;
+          float cs0[8], cs1[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cs0[i] = cs1[i] = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int r = frq + 8 * j;
+            const bool rpad = (padmask >> r) & 1u;
+            const bool rs1 = (seg1 >> r) & 1u;
+            uint8_t* row32 = s32 + r * 128 + (fm & 1) * 8;
+            uint8_t* row16 = s16 + r * 64 + 4 * fm;
+            const uint8_t* rowmk = smk + r * 64 + 4 * fm;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t* src = (j < 2) ? fa : fb;
+              float v0 = __uint_as_float(src[4 * k + 2 * (j & 1)]) + bias8[2 * k];
+              float v1 = __uint_as_float(src[4 * k + 2 * (j & 1) + 1]) + bias8[2 * k + 1];
+              const int o32 = ((2 * k + (fm >> 1)) ^ frq) << 4;
+              const int o16 = (k ^ sw3) << 4;
+              if (f_r32) {
+                const float2 rr = *reinterpret_cast<const float2*>(row32 + o32);
+                v0 += rr.x; v1 += rr.y;
+              }
+              if (f_relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+              uint32_t mk = 0;
+              if (f_msk) mk = *reinterpret_cast<const uint32_t*>(rowmk + o16);
+              if (f_msk && !f_dot) {
+                if (!(bf16_lo(mk) > 0.f)) v0 = 0.f;
+                if (!(bf16_hi(mk) > 0.f)) v1 = 0.f;
+              }
+              if (rpad) { v0 = 0.f; v1 = 0.f; }
+              float c0v = v0, c1v = v1;
+              if (f_dot) { c0v = v0 * bf16_lo(mk); c1v = v1 * bf16_hi(mk); }
+              if (mixed && rs1) { cs1[2 * k] += c0v; cs1[2 * k + 1] += c1v; }
+              else { cs0[2 * k] += c0v; cs0[2 * k + 1] += c1v; }
+              if (f_o32) *reinterpret_cast<float2*>(row32 + o32) = make_float2(v0, v1);
+              if (f_o16) *reinterpret_cast<uint32_t*>(row16 + o16) = pack_bf16x2(v0, v1);
+            }
+          }
+          // one column total per lane; an unmixed warp belongs to exactly one image segment
+          const float t0 = frag_colsum(cs0, lane);
+          const float t1 = mixed ? frag_colsum(cs1, lane) : 0.f;
+          if (tile_ok) {
+            float* dst = p.pool_part + ((long long)tile * 2 * 4 + wq) * 64 + half * 32 + fcol;
+            const bool all1 = seg1 == 0xffffffffu;
+            dst[0] = all1 ? 0.f : t0;
+            dst[4 * 64] = all1 ? t0 : t1;
+          }
+        } else {
         uint32_t raw[16 * NCH];
         if constexpr (N_OUT == 64) {
           tmem_ld32(trow, raw);
@@ -294,7 +453,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tmem_ld16(trow, raw);
         }
         tmem_ld_wait();
-        if (p.tma_epi) {
+        if (f_tma) {
           // ---------------- TMA-staged epilogue (identity mapping, 64 outputs) ----------------
           if (use_in) mbar_wait(bin, it & 1, 6);
           const int sw7 = lane & 7, sw3 = (lane >> 1) & 3;
@@ -306,27 +465,33 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const int c0 = half * 32 + ch * 16;  // first output column of this chunk
             float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[ch * 16 + j]) + s_bias[c0 + j];
-            if (p.use_r32) {
+            for (int j = 0; j < 4; ++j) {   // 128-bit broadcast loads: shared-memory instructions are the scarce resource here
+              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * j);
+              v[4 * j + 0] = __uint_as_float(raw[ch * 16 + 4 * j + 0]) + b4.x;
+              v[4 * j + 1] = __uint_as_float(raw[ch * 16 + 4 * j + 1]) + b4.y;
+              v[4 * j + 2] = __uint_as_float(raw[ch * 16 + 4 * j + 2]) + b4.z;
+              v[4 * j + 3] = __uint_as_float(raw[ch * 16 + 4 * j + 3]) + b4.w;
+            }
+            if (f_r32) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float4 r = *reinterpret_cast<const float4*>(r32 + (((ch * 4 + j) ^ sw7) << 4));
                 v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
               }
             }
-            if (p.resid2 && inrange) {
-              const float4* rp = reinterpret_cast<const float4*>(p.resid2 + (long long)q * 64 + c0);
+            if (f_res2 && inrange) {
+              const float4* rp = reinterpret_cast<const float4*>(f_res2 + (long long)q * 64 + c0);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float4 r = rp[j];
                 v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
               }
             }
-            if (p.flags & SRES_EPI_RELU) {
+            if (f_relu) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
             }
-            if (p.use_msk && !(p.flags & SRES_EPI_DOT)) {
+            if (f_msk && !f_dot) {
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
                 const uint4 mk = *reinterpret_cast<const uint4*>(rmk + (((ch * 2 + j) ^ sw3) << 4));
@@ -342,7 +507,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = 0.f;
             }
-            if (p.flags & SRES_EPI_DOT) {
+            if (f_dot) {
               // per-image channel sums of v * other (the channel-attention backward reduction, fused here)
               float t[16];
 #pragma unroll
@@ -355,22 +520,22 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                   t[8 * j + 2 * e + 1] = v[8 * j + 2 * e + 1] * bf16_hi(w4[e]);
                 }
               }
-              pool_partials(t, seg, lane, p.pool_part + ((long long)tile * 2 * 4 + wq) * 64 + c0);
+              if (tile_ok) pool_partials(t, seg, lane, p.pool_part + ((long long)tile * 2 * 4 + wq) * 64 + c0);
             }
-            if (p.use_o32) {
+            if (f_o32) {
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 *reinterpret_cast<float4*>(r32 + (((ch * 4 + j) ^ sw7) << 4)) =
                     make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
-            if (p.use_o16) {
+            if (f_o16) {
 #pragma unroll
               for (int j = 0; j < 2; ++j)
                 *reinterpret_cast<uint4*>(r16 + (((ch * 2 + j) ^ sw3) << 4)) =
                     make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                                pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
             }
-            if (p.flags & SRES_EPI_POOL)
+            if (f_pool && tile_ok)
               pool_partials(v, seg, lane, p.pool_part + ((long long)tile * 2 * 4 + wq) * 64 + c0);
           }
         } else {
@@ -392,7 +557,13 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const int c0 = half * 32 + ch * 16;
             float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[ch * 16 + j]) + s_bias[c0 + j];
+            for (int j = 0; j < 4; ++j) {   // 128-bit broadcast loads: shared-memory instructions are the scarce resource here
+              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * j);
+              v[4 * j + 0] = __uint_as_float(raw[ch * 16 + 4 * j + 0]) + b4.x;
+              v[4 * j + 1] = __uint_as_float(raw[ch * 16 + 4 * j + 1]) + b4.y;
+              v[4 * j + 2] = __uint_as_float(raw[ch * 16 + 4 * j + 2]) + b4.z;
+              v[4 * j + 3] = __uint_as_float(raw[ch * 16 + 4 * j + 3]) + b4.w;
+            }
             if (p.resid && ovalid) {
               const float4* rp = reinterpret_cast<const float4*>(p.resid + oq * 64 + c0);
 #pragma unroll
@@ -401,15 +572,15 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
               }
             }
-            if (p.resid2 && ovalid) {
-              const float4* rp = reinterpret_cast<const float4*>(p.resid2 + oq * 64 + c0);
+            if (f_res2 && ovalid) {
+              const float4* rp = reinterpret_cast<const float4*>(f_res2 + oq * 64 + c0);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float4 r = rp[j];
                 v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
               }
             }
-            if (p.flags & SRES_EPI_RELU) {
+            if (f_relu) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
             }
@@ -444,43 +615,91 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                      pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
               }
               if (p.out_nchw && !pad) {
-                for (int c = 0; c < p.c_real - c0 && c < 16; ++c)
-                  p.out_nchw[(((long long)b * p.c_real + c0 + c) * p.H + y) * p.W + x] = v[c];
+#pragma unroll
+                for (int c = 0; c < 16; ++c)   // unrolled + predicated: v[] stays in registers
+                  if (c0 + c < p.c_real) p.out_nchw[(((long long)b * p.c_real + c0 + c) * p.H + y) * p.W + x] = v[c];
               }
             }
-            if (p.flags & SRES_EPI_POOL)
+            if (f_pool && tile_ok)
               pool_partials(v, seg, lane, p.pool_part + ((long long)tile * 2 * 4 + wq) * 64 + c0);
           }
+        }
         }
       }
       // accumulator stage drained (all tcgen05.ld of this warp have completed)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_tempty[acc]);
-      if (p.tma_epi) {
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[acc]), 0));
+        else mbar_arrive(&bar_tempty[acc]);
+      }
+      if (f_tma) {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (p.use_o16) tma_store_2d(&tmO16, s16, half * 32, row0);
-          if (p.use_o32) tma_store_2d(&tmO32, s32, half * 32, row0);
+          if (f_o16) tma_store_2d(&tmO16, s16, half * 32, row0);
+          if (f_o32) tma_store_2d(&tmO32, s32, half * 32, row0);
           bulk_commit();
         }
       }
     }
     if (warp == 4) SRES_STAMP(8);
-    if (p.tma_epi && lane == 0) bulk_wait_all<0>();
+    if ((FL >= 0 || p.tma_epi) && lane == 0) bulk_wait_all<0>();
     if (warp == 4) SRES_STAMP(9);
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // neither CTA may leave while the other still signals it / its MMAs run
+  else __syncthreads();
   if (tl && threadIdx.x == 0) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
     tl[11] = (long long)gt;
     tl[12] = clock64();
   }
-  if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_dealloc2(tmem_base, tmem_cols);
+    else tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// launch with programmatic dependent launch and, for the CTA-pair kernel, a cluster dimension of 2
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_conv_kernel(bool pair, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                      Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (pair) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = 2; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+static bool conv_frag_enabled() {
+  static const int on = [] {
+    const char* e = getenv("SRES_CONV_FRAG");
+    return e ? atoi(e) : 1;
+  }();
+  return on != 0;
+}
+
+static bool conv_pair_enabled() {
+  static const int on = [] {
+    const char* e = getenv("SRES_CONV_PAIR");
+    return e ? atoi(e) : 0;  // measured slower than the single-CTA kernel for N = 64
+  }();
+  return on != 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -515,7 +734,9 @@ static int launch_conv(const sres_conv_args* a, cudaStream_t stream) {
     p.use_o16 = a->out_bf16 != nullptr; p.use_msk = a->mask_bf16 != nullptr;
     p.use_r32 = a->resid_f32 != nullptr; p.use_o32 = a->out_f32 != nullptr;
   }
-  const int wbytes = 9 * a->n_out * 128;
+  // CTA pairs for the 64-output convolutions (debug_flags bit 2 forces the single-CTA kernel)
+  const bool pair = a->n_out == 64 && p.n_tiles >= 2 && (conv_pair_enabled() || (a->debug_flags & 8)) && !(a->debug_flags & 4);
+  const int wbytes = 9 * (pair ? a->n_out / 2 : a->n_out) * 128;
   const int smem_max = 232448;  // 227 KB
   const int tail_bytes = 1024;
   int slab_bytes = (p.use_o16 ? 16384 : 0) + (p.use_msk ? 16384 : 0) + ((p.use_r32 | p.use_o32) ? 32768 : 0);
@@ -540,7 +761,7 @@ static int launch_conv(const sres_conv_args* a, cudaStream_t stream) {
   CUtensorMap tmA, tmW, tmO16, tmMsk, tmR32, tmO32;
   int rc = make_tmap_rows64(&tmA, a->in_bf16, (uint64_t)p.npos, kBoxRows);
   if (rc) return rc;
-  rc = make_tmap_rows64(&tmW, a->wpack_bf16, (uint64_t)(9 * a->n_out), a->n_out);
+  rc = make_tmap_rows64(&tmW, a->wpack_bf16, (uint64_t)(9 * a->n_out), pair ? a->n_out / 2 : a->n_out);
   if (rc) return rc;
   tmO16 = tmA; tmMsk = tmA; tmR32 = tmA; tmO32 = tmA;
   if (p.tma_epi) {
@@ -552,28 +773,49 @@ static int launch_conv(const sres_conv_args* a, cudaStream_t stream) {
 
   int sms = device_sm_count();
   if (sms <= 0) return set_error(SRES_ERR_NO_DEVICE, "conv: no CUDA device");
-  const int grid = p.n_tiles < sms ? p.n_tiles : sms;
-  cudaError_t e;
-  static thread_local int attr_dev64 = -1, attr_dev16 = -1;
+  int grid = p.n_tiles < sms ? p.n_tiles : sms;
+  cudaError_t e = cudaSuccess;
   int dev = 0;
   cudaGetDevice(&dev);
-  if (a->n_out == 64) {
-    if (attr_dev64 != dev) {
-      e = cudaFuncSetAttribute(conv3x3_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
-      if (e != cudaSuccess) return set_cuda_error(e, "conv: smem attribute");
-      attr_dev64 = dev;
-    }
-    e = launch_pdl(conv3x3_igemm_kernel<64>, dim3(grid), dim3(kConvThreads), smem, stream, tmA, tmW, tmO16, tmMsk, tmR32, tmO32, p);
-    if (e != cudaSuccess) return set_cuda_error(e, "conv: launch");
-  } else {
-    if (attr_dev16 != dev) {
-      e = cudaFuncSetAttribute(conv3x3_igemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
-      if (e != cudaSuccess) return set_cuda_error(e, "conv: smem attribute");
-      attr_dev16 = dev;
-    }
-    e = launch_pdl(conv3x3_igemm_kernel<16>, dim3(grid), dim3(kConvThreads), smem, stream, tmA, tmW, tmO16, tmMsk, tmR32, tmO32, p);
-    if (e != cudaSuccess) return set_cuda_error(e, "conv: launch");
+  // compile-time flavour of the TMA-staged epilogue, if this call is one of the specialised ones
+  int fl = -1;
+  if (p.tma_epi && !pair && !a->resid2_f32 && !(a->debug_flags & 16)) {
+    fl = (p.use_o16 ? kFlO16 : 0) | (p.use_o32 ? kFlO32 : 0) | (p.use_r32 ? kFlR32 : 0) | (p.use_msk ? kFlMsk : 0) |
+         ((a->epi_flags & SRES_EPI_RELU) ? kFlRelu : 0) | ((a->epi_flags & SRES_EPI_POOL) ? kFlPool : 0) |
+         ((a->epi_flags & SRES_EPI_DOT) ? kFlDot : 0);
+    if ((fl & (kFlPool | kFlDot)) && conv_frag_enabled() && !(a->debug_flags & 32)) fl |= kFlFrag;
   }
+#define SRES_CONV_CASE(NOUT, PAIRED, FLV)                                                                                  \
+  {                                                                                                                      \
+    static thread_local int attr_dev = -1;                                                                               \
+    if (attr_dev != dev) {                                                                                               \
+      e = cudaFuncSetAttribute(conv3x3_igemm_kernel<NOUT, PAIRED, FLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max); \
+      if (e != cudaSuccess) return set_cuda_error(e, "conv: smem attribute");                                           \
+      attr_dev = dev;                                                                                                    \
+    }                                                                                                                    \
+    e = launch_conv_kernel(PAIRED, conv3x3_igemm_kernel<NOUT, PAIRED, FLV>, dim3(grid), dim3(kConvThreads), smem, stream, tmA, \
+                           tmW, tmO16, tmMsk, tmR32, tmO32, p);                                                         \
+  }
+  if (pair) {
+    grid = ((p.n_tiles + 1) / 2 < sms / 2 ? (p.n_tiles + 1) / 2 : sms / 2) * 2;
+    SRES_CONV_CASE(64, true, -1)
+  } else if (a->n_out == 16) {
+    SRES_CONV_CASE(16, false, -1)
+  } else {
+    switch (fl) {
+      case kFlRelu | kFlO16: SRES_CONV_CASE(64, false, kFlRelu | kFlO16) break;                                          // RCAB conv1
+      case kFlPool | kFlO16: SRES_CONV_CASE(64, false, kFlPool | kFlO16) break;                                          // RCAB conv2
+      case kFlPool | kFlO16 | kFlFrag: SRES_CONV_CASE(64, false, kFlPool | kFlO16 | kFlFrag) break;
+      case kFlMsk | kFlO16: SRES_CONV_CASE(64, false, kFlMsk | kFlO16) break;                                            // dgrad of conv2
+      case kFlR32 | kFlO32 | kFlMsk | kFlDot: SRES_CONV_CASE(64, false, kFlR32 | kFlO32 | kFlMsk | kFlDot) break;        // dgrad of conv1
+      case kFlR32 | kFlO32 | kFlMsk | kFlDot | kFlFrag: SRES_CONV_CASE(64, false, kFlR32 | kFlO32 | kFlMsk | kFlDot | kFlFrag) break;
+      case kFlO32 | kFlMsk | kFlDot: SRES_CONV_CASE(64, false, kFlO32 | kFlMsk | kFlDot) break;                          // dgrad of a group tail
+      case kFlO32 | kFlMsk | kFlDot | kFlFrag: SRES_CONV_CASE(64, false, kFlO32 | kFlMsk | kFlDot | kFlFrag) break;
+      default: SRES_CONV_CASE(64, false, -1) break;
+    }
+  }
+#undef SRES_CONV_CASE
+  if (e != cudaSuccess) return set_cuda_error(e, "conv: launch");
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "conv: launch");
   return SRES_OK;

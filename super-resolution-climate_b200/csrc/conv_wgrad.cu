@@ -42,7 +42,8 @@ struct WgradKParams {
 __global__ void __launch_bounds__(256, 1)
 conv3x3_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ CUtensorMap tmPart, const WgradKParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // offset arithmetic (not an integer round trip) keeps the pointer in the shared address space: LDS/STS, not generic LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stage_bytes = (128 + p.xrows) * 128;
   uint8_t* tail = smem + p.nstage * stage_bytes;
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(tail);

@@ -165,8 +165,12 @@ def main():
                  7: "last accumulator ready", 8: "last store issued", 9: "stores drained", 12: "exit"}
         print("per-CTA timeline, cycles since CTA entry (min / median / max over CTAs):")
         for i in (1, 3, 4, 6, 5, 7, 8, 9, 12):
-            d = t[:, i] - t[:, 0]
+            sel = t[:, i] != 0   # the CTA-pair kernel stamps MMA events on leader CTAs only
+            d = (t[:, i] - t[:, 0])[sel]
             print(f"  {names[i]:26s} {d.min():9.0f} {d.median():9.0f} {d.max():9.0f}")
+        for i, nm in ((13, "epilogue warp idle (waits for MMA)"), (14, "MMA warp waits for epilogue"), (15, "MMA warp waits for TMA")):
+            d = t[:, i]
+            print(f"  total cycles: {nm:36s} {d.min():9.0f} {d.median():9.0f} {d.max():9.0f}")
         st = t[:, 10] - g0; en = t[:, 11] - g0
         print(f"globaltimer ns: CTA start min/med/max {st.min():.0f}/{st.median():.0f}/{st.max():.0f}  end {en.min():.0f}/{en.median():.0f}/{en.max():.0f}")
 
