@@ -265,7 +265,7 @@ def run_cuda(args):
     # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of the same kernel/shape
     traffic = None
     try:
-        m = json.load(open(os.path.join(ROOT, "profiles", "r01_v3_conv_ncu_metrics.json")))
+        m = json.load(open(os.path.join(ROOT, "profiles", "r01_v4_conv_ncu_metrics.json")))
         conv = {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Gbyte": 1e9}
         traffic = sum(float(m[k]["value"].replace(",", "")) * conv[m[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
     except Exception:
@@ -282,9 +282,9 @@ def run_cuda(args):
         "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": B * CH * S * S * 4, "d2h_bytes_per_step": 4},
         "gpu_launches": per_step_launches * args.steps,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv3x3_igemm_kernel<64> (64->64 conv, B=64, 48x48)", "achieved": achieved,
+        "roofline": {"bound": "tensor", "kernel": "conv3x3_igemm_kernel<64,false,17> (64->64 conv + bias + ReLU, bf16 out: RCAB conv1, B=64, 48x48)", "achieved": achieved,
                      "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_burst"], "traffic": traffic,
-                     "traffic_note": "DRAM bytes per launch (ncu --set full, profiles/r01_v3_conv_ncu_metrics.json); algorithmic 39.3 MB "
+                     "traffic_note": "DRAM bytes per launch (ncu --set full, profiles/r01_v4_conv_ncu_metrics.json); algorithmic 39.3 MB "
                                      "(19.7 in + 19.7 out): the input is read once, the output is still in L2 when the kernel ends",
                      "peak_source": pk["src"] + " burst (kernel timed alone)", "us_per_launch": conv_ms * 1e3,
                      "step_tflops_per_gpu": step_tflops, "step_frac_of_sustained": step_tflops / pk["tflops_sustained"]},

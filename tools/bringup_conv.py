@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--iters", type=int, default=0)
     ap.add_argument("--bf16-only", action="store_true")
     ap.add_argument("--timeline", action="store_true")
+    ap.add_argument("--relu", action="store_true", help="fwd mode: fuse ReLU (with --bf16-only this is the RCAB conv1 flavour)")
     a = ap.parse_args()
     torch.manual_seed(0)
     torch.backends.cudnn.allow_tf32 = False
@@ -77,6 +78,9 @@ def main():
         if a.bf16_only:
             args.out_f32 = None
         ref = F.conv2d(x, w, bias, padding=1)
+        if a.relu:
+            args.epi_flags = L.EPI_RELU
+            ref = F.relu(ref)
     elif a.mode == "dgrad":
         args.out_f32 = out_f32.data_ptr()
         args.bias = None

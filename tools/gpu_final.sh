@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-end style check: GPU tests, smoke, bench (both arms), ncu launch list, ncu --set full of the conv kernel
+# round-end style check: GPU tests, smoke, bench (both arms), ncu launch list of the bench command
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit=$?" >> gpurun_out/smoke.log
@@ -8,7 +8,4 @@ python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --graph-profiling node -s 9000 -c 3400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu.log 2>&1
-python tools/bringup_conv.py --B 64 --H 48 --W 48 --iters 4 --bf16-only > gpurun_out/plain_conv.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:conv3x3_igemm -s 3 -c 2 -f -o gpurun_out/prof_conv \
-    python tools/bringup_conv.py --B 64 --H 48 --W 48 --iters 4 --bf16-only > gpurun_out/ncu_conv.log 2>&1
 cat gpurun_out/pytest_gpu.log gpurun_out/smoke.log; cat gpurun_out/bench.log | cut -c1-400; tail -n 2 gpurun_out/bench.err

@@ -22,3 +22,12 @@ print(f"\n{sum(v[0] for v in agg.values())} launches, {tot/1e3:.2f} ms of kernel
 print("| share | launches | avg us | kernel |\n|---:|---:|---:|---|")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"| {v[1]/tot*100:.2f}% | {v[0]} | {v[1]/v[0]:.1f} | `{k}` |")
+# template instances of one kernel (epilogue flavours of the conv kernel) summed
+fam = collections.defaultdict(lambda: [0, 0.0])
+for k, v in agg.items():
+    base = re.sub(r"<.*", "", k).replace("void ", "")
+    fam[base][0] += v[0]
+    fam[base][1] += v[1]
+print("\nPer kernel family (all template instances):\n\n| share | launches | avg us | kernel family |\n|---:|---:|---:|---|")
+for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1])[:8]:
+    print(f"| {v[1]/tot*100:.2f}% | {v[0]} | {v[1]/v[0]:.1f} | `{k}` |")
