@@ -63,6 +63,55 @@ def test_conv_forward_bias_relu_pool(env, B, H, W):
         assert rel_l2(sums, ref.sum((2, 3))) < 1e-4
 
 
+@pytest.mark.parametrize("B,H,W", [(3, 20, 24), (5, 48, 48)])
+def test_conv_epilogue_flavours_agree(env, B, H, W):
+    """The compile-time epilogue flavours of the RCAB loop (default), their row-layout variant (debug 32), the generic
+    runtime-flag kernel (debug 16) and the opt-in CTA-pair kernel (debug 8) compute the same thing: outputs bit-equal,
+    per-tile partial sums equal up to summation order."""
+    L, lib, dev = env
+    rows = lib.sres_ptl_rows(B, H, W)
+    nt = lib.sres_conv_mtiles(B, H, W)
+    xin = to_ptl(bf16_round(torch.randn(B, 64, H, W)).to(dev), torch.bfloat16)
+    msk = to_ptl(torch.randn(B, 64, H, W).to(dev), torch.bfloat16)
+    trunk = to_ptl(torch.randn(B, 64, H, W).to(dev), torch.float32)
+    wp = pack(lib, (torch.randn(64, 64, 3, 3) * 0.05).to(dev), 0)
+    bias = torch.randn(64, device=dev)
+    flavours = {
+        "conv1": dict(bias=bias, epi_flags=L.EPI_RELU, o16=True),
+        "conv2": dict(bias=bias, epi_flags=L.EPI_POOL, o16=True, part=True),
+        "dgrad2": dict(mask_bf16=msk, o16=True),
+        "dgrad1": dict(mask_bf16=msk, epi_flags=L.EPI_DOT, o32=True, rmw=True, part=True),
+        "group dgrad": dict(mask_bf16=msk, epi_flags=L.EPI_DOT, o32=True, part=True),
+    }
+    for name, f in flavours.items():
+        results = []
+        for dbg in (0, 32, 16, 8):
+            out16 = torch.full((rows, 64), float("nan"), device=dev, dtype=torch.bfloat16)
+            out32 = trunk.clone() if f.get("rmw") else torch.full((rows, 64), float("nan"), device=dev)
+            part = torch.full((nt, 2, 4, 64), float("nan"), device=dev)
+            kw = dict(in_bf16=xin, wpack_bf16=wp, B=B, H=H, W=W, n_out=64, epi_flags=f.get("epi_flags", 0), debug_flags=dbg)
+            for k in ("bias", "mask_bf16"):
+                if k in f:
+                    kw[k] = f[k]
+            if f.get("o16"):
+                kw["out_bf16"] = out16
+            if f.get("o32"):
+                kw["out_f32"] = out32
+            if f.get("rmw"):
+                kw["resid_f32"] = out32
+            if f.get("part"):
+                kw["pool_part"] = part
+            run_conv(lib, conv_args(**kw))
+            results.append((out16 if f.get("o16") else out32, part))
+        ref_out, ref_part = results[0]
+        assert torch.isfinite(ref_out.float()).all(), name
+        for out, part in results[1:]:
+            assert torch.equal(out, ref_out), name
+            if f.get("part"):
+                # [tile][segment][lane quarter][64]: the second segment only exists for tiles that straddle two images
+                assert rel_l2(part.nan_to_num(0.0).sum(2), ref_part.nan_to_num(0.0).sum(2)) < 1e-5, name
+
+
 @pytest.mark.parametrize("B,H,W", GEOMS[:3])
 def test_conv_dgrad_mask_residuals(env, B, H, W):
     """Input gradient = conv with transposed/flipped weights; ReLU-backward mask; two fp32 addends."""
