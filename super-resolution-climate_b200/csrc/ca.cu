@@ -50,6 +50,44 @@ __device__ __forceinline__ void ca_mlp(const float* __restrict__ w1, const float
   __syncthreads();
 }
 
+// ---- the same MLP with the weights staged in shared memory -----------------------------------
+// The apply kernels sit between two tensor-core kernels and every block repeats the pooled-mean -> MLP chain, so
+// its latency is paid once per RCAB per direction.  Staging the four small parameter arrays with ONE round of global
+// loads (issued together with the loads of the per-tile partial sums) leaves only shared-memory phases in the chain.
+struct CaWeights {
+  float* w1;   // [hid][64]
+  float* w2t;  // [hid][64] (transposed: conflict-free for both products)
+  float* b1;   // [hid]
+  float* b2;   // [64]
+};
+static size_t ca_weights_bytes(int hid) { return (size_t)(2 * hid * 64 + hid + 64) * sizeof(float); }
+__device__ __forceinline__ void ca_stage_weights(CaWeights& S, const float* __restrict__ w1, const float* __restrict__ b1,
+                                                 const float* __restrict__ w2, const float* __restrict__ b2, int hid) {
+  extern __shared__ float ca_dyn_smem[];
+  S.w1 = ca_dyn_smem; S.w2t = S.w1 + hid * 64; S.b1 = S.w2t + hid * 64; S.b2 = S.b1 + hid;
+  for (int i = threadIdx.x; i < hid * 64; i += kCaThreads) {
+    S.w1[i] = __ldg(w1 + i);
+    S.w2t[(i % hid) * 64 + i / hid] = __ldg(w2 + i);
+  }
+  if (threadIdx.x < hid) S.b1[threadIdx.x] = __ldg(b1 + threadIdx.x);
+  if (threadIdx.x < 64) S.b2[threadIdx.x] = __ldg(b2 + threadIdx.x);
+}
+// h = relu(W1 m + b1): one warp per hidden unit.  Caller syncs before (sm_m, weights) and after.
+__device__ __forceinline__ void ca_hidden(const CaWeights& S, int hid, const float* sm_m, float* sm_h) {
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const float m0 = sm_m[lane], m1 = sm_m[lane + 32];
+  for (int j = wrp; j < hid; j += kCaThreads / 32) {
+    const float v = warp_sum(fmaf(S.w1[j * 64 + lane], m0, S.w1[j * 64 + 32 + lane] * m1));
+    if (lane == 0) sm_h[j] = fmaxf(v + S.b1[j], 0.f);
+  }
+}
+// s = sigmoid(W2 h + b2) for channel c = threadIdx.x < 64
+__device__ __forceinline__ float ca_gate(const CaWeights& S, int hid, const float* sm_h, int c) {
+  float z = S.b2[c];
+  for (int j = 0; j < hid; ++j) z = fmaf(S.w2t[j * 64 + c], sm_h[j], z);
+  return 1.f / (1.f + expf(-z));
+}
+
 // ---- stand-alone average-pool sums (used when an image is smaller than one 128-row M tile, where
 // the conv epilogue's two-segment partials do not apply) --------------------------------------
 __global__ void __launch_bounds__(kCaThreads)
@@ -83,11 +121,13 @@ ca_apply_fwd_kernel(CaGeom g, const uint16_t* __restrict__ t2, const float* __re
                     const float* __restrict__ w2, const float* __restrict__ b2, const float* x_in, float* x_out,
                     uint16_t* __restrict__ xb_out, float* __restrict__ save_mean, float* __restrict__ save_s) {
   __shared__ float sm_red[4][64];
-  __shared__ float sm_m[64], sm_h[kCaMaxHidden], sm_z[64], sm_s[64];
-  pdl_wait();
-  pdl_launch_dependents();
+  __shared__ float sm_m[64], sm_h[kCaMaxHidden], sm_s[64];
+  CaWeights sw;
   const int b = blockIdx.y, tid = threadIdx.x;
   const int cg = tid & 7;  // 8-channel slice
+  ca_stage_weights(sw, w1, b1, w2, b2, g.hid);  // parameters are not written by the previous kernel
+  pdl_wait();
+  pdl_launch_dependents();
   const int per_blk = (g.RP + g.blocks_per_image - 1) / g.blocks_per_image;
   const int r0 = blockIdx.x * per_blk + (tid >> 3), r1 = min(g.RP, blockIdx.x * per_blk + per_blk);
   // pooled mean from the conv epilogue partials: tiles covering rows [b*RP, (b+1)*RP)
@@ -97,8 +137,9 @@ ca_apply_fwd_kernel(CaGeom g, const uint16_t* __restrict__ t2, const float* __re
     const int c = tid & 63, part = tid >> 6;  // 4 partial sums per channel
     const int t0 = (b * g.RP) / 128, t1 = ((b + 1) * g.RP - 1) / 128;
     float a = 0.f;
+#pragma unroll 8
     for (int t = t0; t <= t1; ++t) {
-      const int seg = b - (t * 128) / g.RP;  // 0 or 1
+      const int seg = (t * 128 >= b * g.RP) ? 0 : 1;  // a tile that starts in the previous image holds this one as segment 1
       a += pool_part[(((size_t)t * 2 + seg) * 4 + part) * 64 + c];
     }
     sm_red[part][c] = a;
@@ -106,11 +147,17 @@ ca_apply_fwd_kernel(CaGeom g, const uint16_t* __restrict__ t2, const float* __re
   __syncthreads();
   if (tid < 64) sm_m[tid] = (sm_red[0][tid] + sm_red[1][tid] + sm_red[2][tid] + sm_red[3][tid]) / float(g.H * g.W);
   __syncthreads();
-  ca_mlp(w1, b1, w2, b2, g.hid, sm_m, sm_h, sm_z, sm_s);
-  if (blockIdx.x == 0 && tid < 64) {
-    save_mean[b * 64 + tid] = sm_m[tid];
-    save_s[b * 64 + tid] = sm_s[tid];
+  ca_hidden(sw, g.hid, sm_m, sm_h);
+  __syncthreads();
+  if (tid < 64) {
+    const float sg = ca_gate(sw, g.hid, sm_h, tid);
+    sm_s[tid] = sg;
+    if (blockIdx.x == 0) {
+      save_mean[b * 64 + tid] = sm_m[tid];
+      save_s[b * 64 + tid] = sg;
+    }
   }
+  __syncthreads();
   // A thread owns channels [4cg, 4cg+4) and [32+4cg, 32+4cg+4): every load/store instruction of a warp then
   // covers whole contiguous 128-byte (fp32) / 64-byte (bf16) row halves -- fully coalesced per instruction.
   float s8[8];
@@ -175,72 +222,66 @@ ca_bwd_apply_kernel(CaGeom g, const float* __restrict__ grad, const float* __res
                     const float* __restrict__ tile_part, const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                     const float* __restrict__ b2, const float* __restrict__ save_mean,
                     uint16_t* __restrict__ dt2, float* __restrict__ save_ds) {
-  __shared__ float sm_m[64], sm_h[kCaMaxHidden], sm_z[64], sm_s[64], sm_dz[64], sm_dh[kCaMaxHidden], sm_dm[64];
-  pdl_wait();
-  pdl_launch_dependents();
+  __shared__ float sm_m[64], sm_h[kCaMaxHidden], sm_s[64], sm_dz[64], sm_dh[kCaMaxHidden], sm_dm[64];
+  __shared__ float sm_dsr[4][64];
+  CaWeights sw;
   const int b = blockIdx.y, tid = threadIdx.x;
   const int lane = tid & 31, wrp = tid >> 5, cg = tid & 7;
+  ca_stage_weights(sw, w1, b1, w2, b2, g.hid);
+  pdl_wait();
+  pdl_launch_dependents();
   const int per_blk = (g.RP + g.blocks_per_image - 1) / g.blocks_per_image;
   const int r0 = blockIdx.x * per_blk + (tid >> 3), r1 = min(g.RP, blockIdx.x * per_blk + per_blk);
-  float ds = 0.f;
-  __shared__ float sm_dsr[4][64];
   if (tile_part) {  // ds was reduced per M tile by the producing convolution (SRES_EPI_DOT)
     const int c = tid & 63, part = tid >> 6;
     const int t0 = (b * g.RP) / 128, t1 = ((b + 1) * g.RP - 1) / 128;
     float a = 0.f;
+#pragma unroll 8
     for (int t = t0; t <= t1; ++t) {
-      const int seg = b - (t * 128) / g.RP;
+      const int seg = (t * 128 >= b * g.RP) ? 0 : 1;
       a += tile_part[(((size_t)t * 2 + seg) * 4 + part) * 64 + c];
     }
     sm_dsr[part][c] = a;
+  } else if (tid < 64) {
+    float a = 0.f;
+    for (int i = 0; i < g.blocks_per_image; ++i) a += ds_part[((size_t)b * g.blocks_per_image + i) * 64 + tid];
+    sm_dsr[0][tid] = a;
+    sm_dsr[1][tid] = sm_dsr[2][tid] = sm_dsr[3][tid] = 0.f;
   }
+  if (tid < 64) sm_m[tid] = save_mean[b * 64 + tid];
+  __syncthreads();
+  ca_hidden(sw, g.hid, sm_m, sm_h);
   __syncthreads();
   if (tid < 64) {
-    sm_m[tid] = save_mean[b * 64 + tid];
-    if (tile_part) ds = (sm_dsr[0][tid] + sm_dsr[1][tid]) + (sm_dsr[2][tid] + sm_dsr[3][tid]);
-    else
-      for (int i = 0; i < g.blocks_per_image; ++i) ds += ds_part[((size_t)b * g.blocks_per_image + i) * 64 + tid];
+    const float ds = (sm_dsr[0][tid] + sm_dsr[1][tid]) + (sm_dsr[2][tid] + sm_dsr[3][tid]);
     if (blockIdx.x == 0) save_ds[b * 64 + tid] = ds;
+    const float sg = ca_gate(sw, g.hid, sm_h, tid);
+    sm_s[tid] = sg;
+    sm_dz[tid] = ds * sg * (1.f - sg);
   }
   __syncthreads();
-  ca_mlp(w1, b1, w2, b2, g.hid, sm_m, sm_h, sm_z, sm_s);
-  if (tid < 64) {
-    const float s = sm_s[tid];
-    sm_dz[tid] = ds * s * (1.f - s);
+  // dh[j] = relu'(h[j]) * sum_c w2[c][j] dz[c]: one warp per hidden unit
+  for (int j = wrp; j < g.hid; j += kCaThreads / 32) {
+    const float v = warp_sum(fmaf(sw.w2t[j * 64 + lane], sm_dz[lane], sw.w2t[j * 64 + 32 + lane] * sm_dz[lane + 32]));
+    if (lane == 0) sm_dh[j] = sm_h[j] > 0.f ? v : 0.f;
   }
   __syncthreads();
-  {  // dh[j] = relu'(h[j]) * sum_c w2[c][j] dz[c]: thread (j = tid % 64, quarter = tid / 64) sums 16 c's
-    const int j = tid & 63, qd = tid >> 6;
+  if (tid < 64) {  // dm[c] = sum_j w1[j][c] dh[j] / (H*W)
     float a = 0.f;
-    if (j < g.hid)
-      for (int c = qd * 16; c < qd * 16 + 16; ++c) a = fmaf(__ldg(w2 + c * g.hid + j), sm_dz[c], a);
-    __shared__ float sm_part[4][64];
-    sm_part[qd][j] = a;
-    __syncthreads();
-    if (tid < g.hid) sm_dh[tid] = sm_h[tid] > 0.f ? (sm_part[0][tid] + sm_part[1][tid] + sm_part[2][tid] + sm_part[3][tid]) : 0.f;
+    for (int j = 0; j < g.hid; ++j) a = fmaf(sw.w1[j * 64 + tid], sm_dh[j], a);
+    sm_dm[tid] = a / float(g.H * g.W);
   }
   __syncthreads();
-  {  // dm[c] = sum_j w1[j][c] dh[j] / (H*W): coalesced over c, 4 partial sums over j
-    const int c = tid & 63, qd = tid >> 6;
-    float a = 0.f;
-    for (int j = qd; j < g.hid; j += 4) a = fmaf(__ldg(w1 + j * 64 + c), sm_dh[j], a);
-    __shared__ float sm_part2[4][64];
-    sm_part2[qd][c] = a;
-    __syncthreads();
-    if (tid < 64) sm_dm[tid] = (sm_part2[0][tid] + sm_part2[1][tid] + sm_part2[2][tid] + sm_part2[3][tid]) / float(g.H * g.W);
-  }
-  __syncthreads();
-  (void)lane; (void)wrp;
   float s8[8], m8[8];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     s8[j] = sm_s[cg * 4 + j]; s8[4 + j] = sm_s[32 + cg * 4 + j];
     m8[j] = sm_dm[cg * 4 + j]; m8[4 + j] = sm_dm[32 + cg * 4 + j];
   }
+  int y = r0 / g.P, x = r0 - y * g.P;
 #pragma unroll 2
   for (int r = r0; r < r1; r += kCaThreads / 8) {
     const size_t q = (size_t)b * g.RP + r;
-    const int y = r / g.P, x = r - y * g.P;
     uint2 oa = make_uint2(0, 0), ob = make_uint2(0, 0);
     if (x != g.W && y != g.H) {
       const float4 ga = *reinterpret_cast<const float4*>(grad + q * 64 + cg * 4);
@@ -252,6 +293,8 @@ ca_bwd_apply_kernel(CaGeom g, const float* __restrict__ grad, const float* __res
     }
     *reinterpret_cast<uint2*>(dt2 + q * 64 + cg * 4) = oa;
     *reinterpret_cast<uint2*>(dt2 + q * 64 + 32 + cg * 4) = ob;
+    x += kCaThreads / 8;
+    while (x >= g.P) { x -= g.P; ++y; }
   }
 }
 
@@ -382,7 +425,7 @@ extern "C" int sres_ca_apply_fwd(const void* t2_bf16, const float* pool_part, co
   if (!t2_bf16 || (!pool_part && !pool_sum) || !w1 || !b1 || !w2 || !b2 || !x_in || !x_out || !save_mean || !save_s)
     return set_error(SRES_ERR_INVALID_ARG, "ca_apply_fwd: null pointer");
   dim3 grid(g.blocks_per_image, B);
-  cudaError_t e = launch_pdl_if(pdl_level() >= 2, ca_apply_fwd_kernel, grid, dim3(kCaThreads), 0, (cudaStream_t)stream, g, (const uint16_t*)t2_bf16,
+  cudaError_t e = launch_pdl_if(pdl_level() >= 2, ca_apply_fwd_kernel, grid, dim3(kCaThreads), ca_weights_bytes(hidden), (cudaStream_t)stream, g, (const uint16_t*)t2_bf16,
                              pool_part, pool_sum, w1, b1, w2, b2, x_in, x_out, (uint16_t*)xb_out_bf16, save_mean, save_s);
   if (e != cudaSuccess) return set_cuda_error(e, "ca_apply_fwd: launch");
   return SRES_OK;
@@ -400,7 +443,7 @@ extern "C" int sres_ca_bwd(const float* grad_f32, const void* t2_bf16, const flo
   cudaError_t e = launch_pdl_if(pdl_level() >= 2, ca_bwd_reduce_kernel, grid, dim3(kCaThreads), 0, (cudaStream_t)stream, g, grad_f32,
                              (const uint16_t*)t2_bf16, ds_part);
   if (e != cudaSuccess) return set_cuda_error(e, "ca_bwd: reduce launch");
-  e = launch_pdl_if(pdl_level() >= 2, ca_bwd_apply_kernel, grid, dim3(kCaThreads), 0, (cudaStream_t)stream, g, grad_f32, (const float*)ds_part, (const float*)nullptr, w1, b1,
+  e = launch_pdl_if(pdl_level() >= 2, ca_bwd_apply_kernel, grid, dim3(kCaThreads), ca_weights_bytes(hidden), (cudaStream_t)stream, g, grad_f32, (const float*)ds_part, (const float*)nullptr, w1, b1,
                  w2, b2, save_mean, (uint16_t*)dt2_bf16, save_ds);
   if (e != cudaSuccess) return set_cuda_error(e, "ca_bwd: apply launch");
   return SRES_OK;
@@ -416,7 +459,7 @@ extern "C" int sres_ca_bwd_apply(const float* grad_f32, const float* tile_part, 
   if (!grad_f32 || !tile_part || !w1 || !b1 || !w2 || !b2 || !save_mean || !dt2_bf16 || !save_ds)
     return set_error(SRES_ERR_INVALID_ARG, "ca_bwd_apply: null pointer");
   dim3 grid(g.blocks_per_image, B);
-  cudaError_t e = launch_pdl_if(pdl_level() >= 2, ca_bwd_apply_kernel, grid, dim3(kCaThreads), 0, (cudaStream_t)stream, g, grad_f32,
+  cudaError_t e = launch_pdl_if(pdl_level() >= 2, ca_bwd_apply_kernel, grid, dim3(kCaThreads), ca_weights_bytes(hidden), (cudaStream_t)stream, g, grad_f32,
                                 (const float*)nullptr, tile_part, w1, b1, w2, b2, save_mean, (uint16_t*)dt2_bf16, save_ds);
   if (e != cudaSuccess) return set_cuda_error(e, "ca_bwd_apply: launch");
   return SRES_OK;
