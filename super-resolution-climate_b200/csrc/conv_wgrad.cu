@@ -134,8 +134,11 @@ conv3x3_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
     if (leader) umma_commit(bar_done);
   } else if (warp >= 4) {
     // bias gradient: column sums of the dY tile, read straight from the swizzled smem rows.
+    // 128-bit loads: lane = (row group rg = lane / 8, 16-byte chunk ck = lane % 8) -> 4 rows per instruction,
+    // 8 instructions per 32-row slice; the 4 row groups are folded once at the end.
     const int wq = warp & 3;
-    float acc0 = 0.f, acc1 = 0.f;  // channels 2*lane, 2*lane+1 over rows wq*32 .. wq*32+31
+    const int rg = lane >> 3, ck = lane & 7;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // channels 8*ck .. 8*ck+7
     pdl_wait();  // the partial buffers this CTA overwrites may still be read by the previous batch's reduce
     int it = 0;
     for (int c = split; c < p.n_chunks; c += nsplit, ++it) {
@@ -143,19 +146,25 @@ conv3x3_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
       const uint32_t ph = (it / p.nstage) & 1;
       mbar_wait(&bar_full[slot], ph, 13);
       const uint8_t* dy = smem + slot * stage_bytes;
-      const int chunk = lane >> 2, within = (lane & 3) * 4;
-#pragma unroll 8
-      for (int r = 0; r < 32; ++r) {
-        const int row = wq * 32 + r;
-        const uint32_t v = *reinterpret_cast<const uint32_t*>(dy + row * 128 + ((chunk ^ (row & 7)) << 4) + within);
-        acc0 += bf16_lo(v);
-        acc1 += bf16_hi(v);
+#pragma unroll
+      for (int r = 0; r < 32; r += 4) {
+        const int row = wq * 32 + r + rg;
+        const uint4 v = *reinterpret_cast<const uint4*>(dy + row * 128 + ((ck ^ (row & 7)) << 4));
+        acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+        acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_empty[slot]);
     }
-    s_db[wq * 64 + 2 * lane] = acc0;
-    s_db[wq * 64 + 2 * lane + 1] = acc1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+    }
+    if (rg == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_db[wq * 64 + 8 * ck + j] = acc[j];
+    }
     asm volatile("bar.sync 1, 128;" ::: "memory");  // all four warps are done reading the operand ring
     // drain the accumulators: TMEM -> swizzled smem slab (the operand ring is idle now) -> TMA store
     mbar_wait(bar_done, 0, 14);

@@ -30,7 +30,7 @@ int make_tmap_rows64_half(CUtensorMap* out, const void* base, uint64_t nrows, ui
 // the attribute off (plain stream order) for A/B measurements.
 bool l2_hint_enabled();  // true after sres_l2_set_aside(bytes > 0)
 bool pdl_enabled();
-int pdl_level();  // SRES_PDL: 0 = off, 1 = tensor-core kernels only (default), 2 = also the element-wise kernels
+int pdl_level();  // SRES_PDL: 0 = off, 1 = tensor-core kernels only, 2 = also the channel-attention kernels (default)
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl_if(bool on, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg{};
