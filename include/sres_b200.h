@@ -137,6 +137,7 @@ typedef struct sres_wgrad_job {
   float* dw_oihw;          /* fp32 (cout_total, 64, 3, 3)                                        */
   float* dbias;            /* fp32 (cout_total) or NULL                                          */
   int32_t cout_total, oc_stride, oc_offset, accumulate;
+  float scale;             /* result multiplier (1 for a plain conv; EDSR's res_scale for conv2) */
 } sres_wgrad_job;
 SRES_API int sres_conv3x3_wgrad_batch(const sres_wgrad_job* jobs, int njobs, int B, int H, int W, void* workspace,
                                       size_t workspace_bytes, void* stream);
@@ -229,7 +230,12 @@ SRES_API int sres_adam_step_flat(float* p, const float* g, float* m, float* v, i
 
 /* ------------------------------------------------------------------------------------------ */
 /* Whole network: RCAN forward / backward  (sres/model/rcan/network.py:9-27)                   */
+/*   and EDSR through the same entry points (sres/model/edsr/network.py:9-32: head conv,       */
+/*   n_blocks x ResBlock(conv, ReLU, conv, *res_scale, +x) common/residual.py:30-54, conv,      */
+/*   +head, SPUpsample common/upsample.py:34-66, conv)                                          */
 /* ------------------------------------------------------------------------------------------ */
+#define SRES_ARCH_RCAN 0
+#define SRES_ARCH_EDSR 1
 typedef struct sres_rcan_desc {
   int32_t B, H, W;         /* low-resolution tile batch                                         */
   int32_t cin, cout;       /* image channels (nchannels_in / nchannels_out, manager.py:52)       */
@@ -239,6 +245,9 @@ typedef struct sres_rcan_desc {
   int32_t reduction;       /* cbottleneck                                                        */
   int32_t n_up;            /* upsampler stages                                                   */
   int32_t up_factor[4];    /* PixelShuffle factor of each stage: 2,2 for x4; 3 for x3            */
+  int32_t arch;            /* SRES_ARCH_RCAN (0) or SRES_ARCH_EDSR: n_groups = 1, n_blocks = nlayers, */
+                           /* reduction ignored                                                  */
+  float res_scale;         /* EDSR only: ResBlock residual scaling (edsr.yaml res_scale)         */
 } sres_rcan_desc;
 
 /* Parameters / gradients are ONE flat fp32 buffer in the reference's state_dict order.        */
@@ -254,7 +263,7 @@ SRES_API int sres_rcan_pack_weights(const sres_rcan_desc* d, const float* params
 SRES_API int sres_rcan_forward(const sres_rcan_desc* d, const float* params, const float* x_nchw, float* out_nchw,
                                void* workspace, int training, void* stream);
 /* Backward in segments [seg_begin, seg_end): 0 = tail + upsampler + body-tail conv,
- * 1..G = residual groups G-1..0, G+1 = head conv.  Each segment completes the gradients of the
+ * 1..G = residual groups G-1..0 (EDSR: 1 = all ResBlocks), G+1 = head conv.  Each segment completes the gradients of the
  * parameter range reported by sres_rcan_segment_params, so a data-parallel caller can start
  * the all-reduce of that range while the next segment runs.                                     */
 SRES_API int sres_rcan_num_segments(const sres_rcan_desc* d);

@@ -19,14 +19,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import ref_import as R  # noqa: E402
 import rcan_oracle as O  # noqa: E402
-from synth import MODEL_CASES, TASK, TILE_CASES, sha, synth_hr, synth_region  # noqa: E402
+from synth import MODEL_CASES, TASK, TILE_CASES, golden_file, sha, synth_hr, synth_region  # noqa: E402
 
 GOLD = os.path.join(HERE, "..", "tests", "golden")
 
 def gen_model_case(name, over, B, S, C, loss_name, smooth, full_out):
     cfg = O.model_cfg(**over)
     R.set_cfg(cfg, TASK)
-    from sres.model.rcan.network import get_model
+    import importlib
+    get_model = importlib.import_module(f"sres.model.{cfg['name']}.network").get_model  # manager.py:93-95
     from sres.base.util import array as ref_array
     from sres.controller.stats import l2loss as ref_l2
     from sres.controller.dual_trainer import ModelTrainer
@@ -66,15 +67,21 @@ def gen_model_case(name, over, B, S, C, loss_name, smooth, full_out):
         post_norms=np.array([post[k].double().norm().item() for k in grads.keys()]),
         grad_global_norm=np.float64(torch.sqrt(sum(g.double().pow(2).sum() for g in grads.values())).item()),
     )
-    keep = ["head.0.weight", "head.0.bias", "tail.1.weight", "tail.1.bias", "body.0.body.0.body.0.bias",
-            "body.0.body.0.body.3.conv_du.0.weight", "body.0.body.0.body.3.conv_du.2.bias", f"body.{cfg['nlayers']}.bias"]
+    if O.is_edsr(cfg):
+        keep = ["head.0.weight", "head.0.bias", "tail.1.weight", "tail.1.bias", "body.0.body.0.bias", "body.0.body.2.bias",
+                f"body.{cfg['nlayers']}.bias"]
+        w2 = "body.0.body.2.weight"
+    else:
+        keep = ["head.0.weight", "head.0.bias", "tail.1.weight", "tail.1.bias", "body.0.body.0.body.0.bias",
+                "body.0.body.0.body.3.conv_du.0.weight", "body.0.body.0.body.3.conv_du.2.bias", f"body.{cfg['nlayers']}.bias"]
+        w2 = "body.0.body.0.body.2.weight"
     for k in keep:
         out["grad::" + k] = grads[k].numpy()
         out["post::" + k] = post[k].numpy()
-    w = grads["body.0.body.0.body.2.weight"].numpy()
-    out["grad::body.0.body.0.body.2.weight[:8,:8]"] = w[:8, :8]
-    np.savez_compressed(os.path.join(GOLD, f"rcan_{name}.npz"), **out)
-    print(f"rcan_{name}: loss={out['loss']:.6f} |out|={out['output_norm']:.4f} |g|={out['grad_global_norm']:.4e}")
+    w = grads[w2].numpy()
+    out[f"grad::{w2}[:8,:8]"] = w[:8, :8]
+    np.savez_compressed(os.path.join(GOLD, golden_file(name)), **out)
+    print(f"{golden_file(name)}: loss={out['loss']:.6f} |out|={out['output_norm']:.4f} |g|={out['grad_global_norm']:.4e}")
 
 
 def gen_tiles_case(name, C, Y, X, tile, scale, seed, same_mask):
@@ -149,10 +156,12 @@ def gen_tiles_case(name, C, Y, X, tile, scale, seed, same_mask):
 
 def main():
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["model", "tiles"]
+    which = sys.argv[1:] or ["model", "tiles"]   # e.g. `gen_golden.py model edsr_tiny_x4` regenerates one model case
     if "model" in which:
+        only = [a for a in which if a in MODEL_CASES]
         for name, case in MODEL_CASES.items():
-            gen_model_case(name, *case)
+            if not only or name in only:
+                gen_model_case(name, *case)
     if "tiles" in which:
         for name, case in TILE_CASES.items():
             gen_tiles_case(name, *case)

@@ -7,6 +7,9 @@ CUDA library.
 What it restates (plain fp32 PyTorch on the CPU, the same third-party arithmetic the reference
 executes -- the reference pins no torch version, README.md:14; this image has torch 2.11.0):
 
+  edsr_forward            sres/model/edsr/network.py:27-32 (EDSR.forward), sres/model/common/residual.py:50-54
+                          (ResBlock: conv, ReLU, conv, .mul(res_scale), += x), sres/model/common/upsample.py:34-66
+                          (SPUpsample, same layers as the RCAN Upsampler).  Selected by cfg["name"] == "edsr".
   rcan_forward            sres/model/rcan/network.py:22-27 (RCAN.forward), :44-47 (CALayer),
                           :61-64 (RCAB), :74-77 (ResidualGroup); sres/model/rcan/blocks.py:58-76
                           (Upsampler = [conv F->4F, PixelShuffle(2)] x log2(scale), or conv F->9F +
@@ -41,10 +44,20 @@ DEFAULT_MODEL_CFG = dict(  # config/model/rcan-10-20-64.yaml
 )
 
 
+EDSR_MODEL_CFG = dict(  # config/model/edsr.yaml
+    name="edsr", nlayers=16, nfeatures=64, kernel_size=3, bias=True, res_scale=1.0, batch_norm=False,
+    downscale_factors=[2, 2], loss_fn="l2",
+)
+
+
 def model_cfg(**over):
-    cfg = dict(DEFAULT_MODEL_CFG)
+    cfg = dict(EDSR_MODEL_CFG if over.get("name") == "edsr" else DEFAULT_MODEL_CFG)
     cfg.update(over)
     return cfg
+
+
+def is_edsr(cfg) -> bool:
+    return cfg.get("name", "rcan") == "edsr"
 
 
 def scale_of(cfg) -> int:
@@ -61,15 +74,26 @@ def upsampler_stages(scale: int) -> List[int]:
 
 
 def param_shapes(cfg, nchannels_in: int, nchannels_out: int) -> Dict[str, tuple]:
-    """Ordered {state_dict key: shape} of the reference RCAN (network.py:9-20)."""
-    Fn, G, R, k = cfg["nfeatures"], cfg["nlayers"], cfg["nblocks"], cfg["kernel_size"]
-    red = cfg["cbottleneck"]
+    """Ordered {state_dict key: shape} of the reference RCAN (network.py:9-20) / EDSR (edsr/network.py:14-26)."""
     shapes: Dict[str, tuple] = {}
 
     def conv(name, cout, cin, ks):
         shapes[name + ".weight"] = (cout, cin, ks, ks)
         shapes[name + ".bias"] = (cout,)
 
+    if is_edsr(cfg):
+        Fn, N, k = cfg["nfeatures"], cfg["nlayers"], cfg["kernel_size"]
+        conv("head.0", Fn, nchannels_in, k)
+        for r in range(N):
+            conv(f"body.{r}.body.0", Fn, Fn, k)
+            conv(f"body.{r}.body.2", Fn, Fn, k)
+        conv(f"body.{N}", Fn, Fn, k)
+        for i, f in enumerate(upsampler_stages(scale_of(cfg))):
+            conv(f"tail.0.{2 * i}", f * f * Fn, Fn, 3)
+        conv("tail.1", nchannels_out, Fn, k)
+        return shapes
+    Fn, G, R, k = cfg["nfeatures"], cfg["nlayers"], cfg["nblocks"], cfg["kernel_size"]
+    red = cfg["cbottleneck"]
     conv("head.0", Fn, nchannels_in, k)
     for g in range(G):
         for r in range(R):
@@ -145,6 +169,27 @@ def rcan_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], cfg) -> torch.Ten
     return _conv(res, sd, "tail.1", pad)
 
 
+def edsr_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], cfg) -> torch.Tensor:
+    """EDSR.forward, edsr/network.py:27-32; ResBlock.forward, common/residual.py:50-54."""
+    N, k, rs = cfg["nlayers"], cfg["kernel_size"], cfg.get("res_scale", 1.0)
+    pad = k // 2
+    x = _conv(x, sd, "head.0", pad)
+    res = x
+    for r in range(N):
+        t = F.relu(_conv(res, sd, f"body.{r}.body.0", pad))
+        t = _conv(t, sd, f"body.{r}.body.2", pad).mul(rs)
+        res = t + res
+    res = _conv(res, sd, f"body.{N}", pad)
+    res = res + x
+    for i, f in enumerate(upsampler_stages(scale_of(cfg))):
+        res = F.pixel_shuffle(_conv(res, sd, f"tail.0.{2 * i}", 1), f)
+    return _conv(res, sd, "tail.1", pad)
+
+
+def model_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], cfg) -> torch.Tensor:
+    return edsr_forward(x, sd, cfg) if is_edsr(cfg) else rcan_forward(x, sd, cfg)
+
+
 # ---------------------------------------------------------------------------------------------
 # interpolation and losses
 # ---------------------------------------------------------------------------------------------
@@ -195,7 +240,7 @@ def single_product_loss(prd, tar, name="l2"):
 def apply_network(hr: torch.Tensor, sd, cfg):
     """dual_trainer.py:557-571: (input, product, target) from an HR batch."""
     lr = downsample(hr, scale_of(cfg))
-    return lr, rcan_forward(lr, sd, cfg), hr
+    return lr, model_forward(lr, sd, cfg), hr
 
 
 class AdamState:
@@ -240,11 +285,16 @@ def train_step(hr, sd, cfg, adam: AdamState, loss_name: Optional[str] = None):
 
 def flops_per_tile(cfg, cin, cout, S=48, train=False):
     """Algorithmic FLOPs per LR tile of S x S."""
-    Fn, G, R, red = cfg["nfeatures"], cfg["nlayers"], cfg["nblocks"], cfg["cbottleneck"]
+    if is_edsr(cfg):
+        Fn, G, R, red = cfg["nfeatures"], 0, 0, 1
+        nbody = 2 * cfg["nlayers"] + 1
+    else:
+        Fn, G, R, red = cfg["nfeatures"], cfg["nlayers"], cfg["nblocks"], cfg["cbottleneck"]
+        nbody = G * (2 * R + 1) + 1
     s = scale_of(cfg)
     ups, px = 0, 1
     for f in upsampler_stages(s):
         ups += f * f * Fn * Fn * px
         px *= f * f
-    fwd = 2 * 9 * S * S * (cin * Fn + (G * (2 * R + 1) + 1) * Fn * Fn + ups + Fn * cout * s * s) + G * R * 4 * Fn * Fn / red
+    fwd = 2 * 9 * S * S * (cin * Fn + nbody * Fn * Fn + ups + Fn * cout * s * s) + G * R * 4 * Fn * Fn / red
     return fwd * (3 if train else 1)

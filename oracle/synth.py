@@ -41,7 +41,16 @@ MODEL_CASES = {
     "tiny_x8_4ch": (dict(nlayers=1, nblocks=1, downscale_factors=[2, 2, 2]), 1, 8, 4, "l2", False, True),
     "tiny_x3": (dict(nlayers=1, nblocks=1, downscale_factors=[3]), 2, 9, 2, "l2", False, True),
     "small_x4": (dict(nlayers=4, nblocks=4), 4, 48, 2, "l2", True, False),
+    # EDSR through the same factory (sres/model/edsr/network.py)
+    "edsr_tiny_x4": (dict(name="edsr", nlayers=3), 2, 12, 2, "l2", False, True),
+    "edsr_x2_rs01_charb": (dict(name="edsr", nlayers=2, res_scale=0.1, downscale_factors=[2], loss_fn="charbonnier"), 3, 10, 1,
+                           "charbonnier", True, True),
+    "edsr_16_x4": (dict(name="edsr", nlayers=16), 2, 48, 2, "l2", True, False),
 }
+
+
+def golden_file(name: str) -> str:
+    return f"{name}.npz" if name.startswith("edsr_") else f"rcan_{name}.npz"
 
 
 def synth_region(C, Y, X, seed, nan_frac=0.2):

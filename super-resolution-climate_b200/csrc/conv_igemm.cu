@@ -809,6 +809,7 @@ static int launch_conv(const sres_conv_args* a, cudaStream_t stream) {
       case kFlMsk | kFlO16: SRES_CONV_CASE(64, false, kFlMsk | kFlO16) break;                                            // dgrad of conv2
       case kFlR32 | kFlO32 | kFlMsk | kFlDot: SRES_CONV_CASE(64, false, kFlR32 | kFlO32 | kFlMsk | kFlDot) break;        // dgrad of conv1
       case kFlR32 | kFlO32 | kFlMsk | kFlDot | kFlFrag: SRES_CONV_CASE(64, false, kFlR32 | kFlO32 | kFlMsk | kFlDot | kFlFrag) break;
+      case kFlR32 | kFlO32 | kFlO16: SRES_CONV_CASE(64, false, kFlR32 | kFlO32 | kFlO16) break;                          // EDSR conv2 / conv1 dgrad
       case kFlO32 | kFlMsk | kFlDot: SRES_CONV_CASE(64, false, kFlO32 | kFlMsk | kFlDot) break;                          // dgrad of a group tail
       case kFlO32 | kFlMsk | kFlDot | kFlFrag: SRES_CONV_CASE(64, false, kFlO32 | kFlMsk | kFlDot | kFlFrag) break;
       default: SRES_CONV_CASE(64, false, -1) break;

@@ -212,6 +212,7 @@ struct WgReduceJob {
   float* dw;
   float* db;
   int cout_total, oc_stride, oc_offset, accumulate, nsplit;
+  float scale;
 };
 struct WgReduceJobs {
   WgReduceJob j[kWgMaxJobs];
@@ -229,6 +230,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, const float*
     const int co = idx - kWgPartFloats;
     float s = 0.f;
     for (int i = 0; i < J.nsplit; ++i) s += part_bias[((size_t)job * max_split + i) * 64 + co];
+    s *= J.scale;
     const int oc = co * J.oc_stride + J.oc_offset;
     if (J.db && oc < J.cout_total) J.db[oc] = J.accumulate ? J.db[oc] + s : s;
     return;
@@ -236,6 +238,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, const float*
   float s = 0.f;
   const float* pp = part + (size_t)job * max_split * kWgPartFloats + idx;
   for (int i = 0; i < J.nsplit; ++i) s += pp[(size_t)i * kWgPartFloats];
+  s *= J.scale;
   const int n = idx & 63;
   const int m = (idx >> 6) & 127;
   const int a = idx >> 13;
@@ -313,6 +316,7 @@ extern "C" int sres_conv3x3_wgrad_batch(const sres_wgrad_job* jobs, int njobs, i
     if (rc) return rc;
     rj.j[j].dw = J.dw_oihw; rj.j[j].db = J.dbias; rj.j[j].cout_total = J.cout_total; rj.j[j].oc_stride = J.oc_stride;
     rj.j[j].oc_offset = J.oc_offset; rj.j[j].accumulate = J.accumulate;
+    rj.j[j].scale = J.scale;
     rj.j[j].nsplit = j < njobs ? (grid - j + njobs - 1) / njobs : 0;
   }
   CUtensorMap tmPart;
@@ -336,5 +340,6 @@ extern "C" int sres_conv3x3_wgrad(const void* x_bf16, const void* dy_bf16, int B
   sres_wgrad_job j;
   j.x_bf16 = x_bf16; j.dy_bf16 = dy_bf16; j.dw_oihw = dw_oihw; j.dbias = dbias;
   j.cout_total = cout_total; j.oc_stride = oc_stride; j.oc_offset = oc_offset; j.accumulate = accumulate;
+  j.scale = 1.f;
   return sres_conv3x3_wgrad_batch(&j, 1, B, H, W, workspace, workspace_bytes, stream);
 }

@@ -59,6 +59,9 @@ struct ProfScope {
 
 struct Net {
   sres_rcan_desc d;
+  bool edsr;    // EDSR: one "group" of ResBlocks without channel attention, group-tail conv or group skip
+  float rs;     // EDSR residual scaling (1 for RCAN)
+  int per;      // 64->64 convs per group in the packed-weight tables: 2R (+1 group-tail conv for RCAN)
   int hid;
   // parameter offsets (floats)
   long long head_w, head_b, body0, rcab_sz, group_sz, bt_w, bt_b, up_w[4], up_b[4], tail_w, tail_b, n_params;
@@ -70,12 +73,13 @@ struct Net {
   size_t o_wp_fwd, o_wp_dg, o_wp_up_fwd[4], o_wp_up_dg[4], o_wp_tail, o_bias_up[4], o_bias_tail;
   size_t o_xb, o_t1, o_t2, o_mean, o_s, o_ds, o_resb, o_u[4];
   size_t o_hf, o_gf[2], o_xf, o_pool_part, o_pool_sum;
+  size_t o_sbias;  // EDSR: res_scale * bias of every ResBlock's second conv
   size_t o_ga, o_gb32, o_gb16, o_dt2[3], o_dt1[3], o_ds_part, o_wg_ws, o_sw_ws, o_ca_scr, o_du16[4], o_du32[4], o_dres32, o_dres16;
   size_t total;
   int n_xb, n_t;  // saved-buffer counts (1 in inference mode)
-  long long cidx(int g, int r, int which) const { return (long long)g * (2 * d.n_blocks + 1) + 2 * r + which; }
-  long long cidx_gt(int g) const { return (long long)g * (2 * d.n_blocks + 1) + 2 * d.n_blocks; }
-  long long cidx_bt() const { return (long long)d.n_groups * (2 * d.n_blocks + 1); }
+  long long cidx(int g, int r, int which) const { return (long long)g * per + 2 * r + which; }
+  long long cidx_gt(int g) const { return (long long)g * per + 2 * d.n_blocks; }
+  long long cidx_bt() const { return (long long)d.n_groups * per; }
   long long off_rcab(int g, int r) const { return body0 + g * group_sz + r * rcab_sz; }
   long long off_gt(int g) const { return body0 + g * group_sz + d.n_blocks * rcab_sz; }
 };
@@ -89,18 +93,25 @@ static int build_net(Net* n, const sres_rcan_desc* d, int training) {
   if (d->cin < 1 || d->cin > 4 || d->cout < 1 || d->cout > 4)
     return set_error(SRES_ERR_UNSUPPORTED, "rcan: 1..4 image channels supported");
   if (d->n_groups < 1 || d->n_blocks < 1) return set_error(SRES_ERR_INVALID_ARG, "rcan: need >= 1 group and block");
-  if (d->reduction < 1 || 64 % d->reduction) return set_error(SRES_ERR_INVALID_ARG, "rcan: reduction must divide 64");
+  if (d->arch != SRES_ARCH_RCAN && d->arch != SRES_ARCH_EDSR) return set_error(SRES_ERR_INVALID_ARG, "rcan: unknown arch");
+  const bool edsr = d->arch == SRES_ARCH_EDSR;
+  if (!edsr && (d->reduction < 1 || 64 % d->reduction)) return set_error(SRES_ERR_INVALID_ARG, "rcan: reduction must divide 64");
+  if (edsr && d->n_groups != 1) return set_error(SRES_ERR_INVALID_ARG, "edsr: n_groups must be 1 (n_blocks = number of ResBlocks)");
+  if (edsr && !(d->res_scale > 0.f)) return set_error(SRES_ERR_INVALID_ARG, "edsr: res_scale must be positive");
   if (d->n_up < 0 || d->n_up > 4) return set_error(SRES_ERR_UNSUPPORTED, "rcan: at most 4 upsampler stages");
   memset(n, 0, sizeof(*n));
   n->d = *d;
-  n->hid = 64 / d->reduction;
+  n->edsr = edsr;
+  n->rs = edsr ? d->res_scale : 1.f;
+  n->hid = edsr ? 0 : 64 / d->reduction;
+  n->per = 2 * d->n_blocks + (edsr ? 0 : 1);
   const int G = d->n_groups, R = d->n_blocks, hid = n->hid;
   long long o = 0;
   n->head_w = o; o += 64LL * d->cin * 9;
   n->head_b = o; o += 64;
   n->body0 = o;
-  n->rcab_sz = 2LL * (kConvW + 64) + (hid * 64 + hid) + (64 * hid + 64);
-  n->group_sz = R * n->rcab_sz + kConvW + 64;
+  n->rcab_sz = 2LL * (kConvW + 64) + (edsr ? 0 : (hid * 64 + hid) + (64 * hid + 64));
+  n->group_sz = R * n->rcab_sz + (edsr ? 0 : kConvW + 64);
   o += G * n->group_sz;
   n->bt_w = o; o += kConvW;
   n->bt_b = o; o += 64;
@@ -115,7 +126,7 @@ static int build_net(Net* n, const sres_rcan_desc* d, int training) {
   n->tail_w = o; o += (long long)d->cout * 64 * 9;
   n->tail_b = o; o += d->cout;
   n->n_params = o;
-  n->n_body_convs = G * (2 * R + 1) + 1;
+  n->n_body_convs = G * n->per + 1;
   for (int i = 0; i <= d->n_up; ++i) {
     n->lvRows[i] = (long long)d->B * (n->lvH[i] + 1) * (n->lvW[i] + 1);
     if (n->lvRows[i] > 0x7fffff00LL) return set_error(SRES_ERR_UNSUPPORTED, "rcan: batch too large");
@@ -140,9 +151,13 @@ static int build_net(Net* n, const sres_rcan_desc* d, int training) {
   n->n_t = training ? G * R : 1;
   n->o_xb = take((size_t)n->n_xb * bf);
   n->o_t1 = take((size_t)n->n_t * bf);
-  n->o_t2 = take((size_t)n->n_t * bf);
-  n->o_mean = take((size_t)n->n_t * d->B * 64 * 4);
-  n->o_s = take((size_t)n->n_t * d->B * 64 * 4);
+  if (edsr) {
+    n->o_sbias = take((size_t)R * 64 * 4);
+  } else {
+    n->o_t2 = take((size_t)n->n_t * bf);
+    n->o_mean = take((size_t)n->n_t * d->B * 64 * 4);
+    n->o_s = take((size_t)n->n_t * d->B * 64 * 4);
+  }
   n->o_resb = take(bf);
   for (int i = 0; i < d->n_up; ++i) n->o_u[i] = take((size_t)n->lvRows[i + 1] * 128);
   n->o_hf = take(f32);
@@ -152,16 +167,19 @@ static int build_net(Net* n, const sres_rcan_desc* d, int training) {
   n->o_pool_part = take((size_t)((r0 + 127) / 128) * 2 * 4 * 64 * 4);
   n->o_pool_sum = take((size_t)d->B * 64 * 4);
   if (training) {
-    n->o_ds = take((size_t)n->n_t * d->B * 64 * 4);
     n->o_ga = take(f32);
-    n->o_gb32 = take(f32);
     n->o_gb16 = take(bf);
+    // rings of 3: the deferred weight-gradient jobs still read a buffer while the next two are produced
     for (int k = 0; k < 3; ++k) { n->o_dt2[k] = take(bf); n->o_dt1[k] = take(bf); }
-    const int bpi = sres_ca_blocks_per_image(d->B, d->H, d->W);
-    n->o_ds_part = take((size_t)d->B * (bpi > 0 ? bpi : 1) * 64 * 4);
+    if (!edsr) {
+      n->o_ds = take((size_t)n->n_t * d->B * 64 * 4);
+      n->o_gb32 = take(f32);
+      const int bpi = sres_ca_blocks_per_image(d->B, d->H, d->W);
+      n->o_ds_part = take((size_t)d->B * (bpi > 0 ? bpi : 1) * 64 * 4);
+      n->o_ca_scr = take(sres_ca_param_grads_scratch_bytes(R, d->B));
+    }
     n->o_wg_ws = take(sres_conv_wgrad_workspace_bytes());
     n->o_sw_ws = take(sres_small_wgrad_workspace_bytes());
-    n->o_ca_scr = take(sres_ca_param_grads_scratch_bytes(R, d->B));
     for (int i = 0; i < d->n_up; ++i) {
       // gradient w.r.t. U[i] (level i+1), stored as f*f sub-grids of level-i rows (PixelUnshuffle layout)
       const int f2 = d->up_factor[i] * d->up_factor[i];
@@ -181,25 +199,33 @@ static int build_net(Net* n, const sres_rcan_desc* d, int training) {
 struct PackBody {
   const float* params;
   long long body0, rcab_sz, group_sz, bt_w;
-  int G, R;
+  int G, R, per;
+  float scale2;     // multiplier folded into every block's second conv (EDSR res_scale; 1 for RCAN)
+  float* sbias;     // EDSR: scale2 * bias of the second convs, [R][64]
   uint16_t* fwd;
   uint16_t* dg;
 };
 __global__ void pack_body_kernel(PackBody pb) {
   const int conv = blockIdx.y;
-  const int per = 2 * pb.R + 1;
+  const int per = pb.per;
   long long off;
+  float sc = 1.f;
   if (conv == pb.G * per) off = pb.bt_w;
   else {
     const int g = conv / per, k = conv % per;
     off = pb.body0 + g * pb.group_sz + (k < 2 * pb.R ? (k / 2) * pb.rcab_sz + (k & 1) * (kConvW + 64) : pb.R * pb.rcab_sz);
+    if (k < 2 * pb.R && (k & 1)) {
+      sc = pb.scale2;
+      if (pb.sbias && blockIdx.x == 0 && threadIdx.x < 64)
+        pb.sbias[(size_t)(g * pb.R + k / 2) * 64 + threadIdx.x] = sc * pb.params[off + kConvW + threadIdx.x];
+    }
   }
   const float* w = pb.params + off;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < kConvW; idx += gridDim.x * blockDim.x) {
     const int k = idx & 63, n = (idx >> 6) & 63, t = idx >> 12;
     const int ky = t / 3, kx = t % 3;
-    const float vf = w[((n * 64 + k) * 3 + ky) * 3 + kx];
-    const float vd = w[((k * 64 + n) * 3 + (2 - ky)) * 3 + (2 - kx)];
+    const float vf = sc * w[((n * 64 + k) * 3 + ky) * 3 + kx];
+    const float vd = sc * w[((k * 64 + n) * 3 + (2 - ky)) * 3 + (2 - kx)];
     pb.fwd[(size_t)conv * kConvW + idx] = (uint16_t)(pack_bf16x2(vf, 0.f) & 0xFFFF);
     pb.dg[(size_t)conv * kConvW + idx] = (uint16_t)(pack_bf16x2(vd, 0.f) & 0xFFFF);
   }
@@ -214,8 +240,8 @@ __global__ void gather_bias_kernel(const float* __restrict__ b, float* __restric
 }
 
 static int pack_all(const Net& n, const float* params, uint8_t* ws, cudaStream_t st) {
-  PackBody pb{params, n.body0, n.rcab_sz, n.group_sz, n.bt_w, n.d.n_groups, n.d.n_blocks,
-              (uint16_t*)(ws + n.o_wp_fwd), (uint16_t*)(ws + n.o_wp_dg)};
+  PackBody pb{params, n.body0, n.rcab_sz, n.group_sz, n.bt_w, n.d.n_groups, n.d.n_blocks, n.per, n.rs,
+              n.edsr ? (float*)(ws + n.o_sbias) : nullptr, (uint16_t*)(ws + n.o_wp_fwd), (uint16_t*)(ws + n.o_wp_dg)};
   pack_body_kernel<<<dim3(8, n.n_body_convs), 256, 0, st>>>(pb);
   SRES_CHECK_LAUNCH("rcan: pack launch");
   for (int i = 0; i < n.d.n_up; ++i) {
@@ -281,7 +307,17 @@ static int forward(const Net& n, const float* P, const float* x, float* out, uin
   if (l2hint) RC(sres_l2_persist_window(xf, (size_t)n.lvRows[0] * 256, st));
   { PROF("head conv"); RC(sres_conv3x3_small_in(x, P + n.head_w, P + n.head_b, B, d.cin, H, W, 0, 0, hf, XB(0), st)); }
   const float* gin = hf;
-  for (int g = 0; g < G; ++g) {
+  if (n.edsr) {
+    // ResBlock r: t1 = relu(conv1(x)); x <- x + res_scale * conv2(t1)   (scale folded into the packed weights / bias)
+    for (int r = 0; r < R; ++r) {
+      const float* pr = P + n.off_rcab(0, r);
+      RC(conv64(XB(xbi), WF(n.cidx(0, r, 0)), pr + kConvW, B, H, W, st, nullptr, T1(r), SRES_EPI_RELU));
+      RC(conv64(T1(r), WF(n.cidx(0, r, 1)), (const float*)(ws + n.o_sbias) + (size_t)r * 64, B, H, W, st, xf, XB(xbi + 1), 0,
+                nullptr, r == 0 ? hf : xf));
+      ++xbi;
+    }
+  }
+  for (int g = 0; g < (n.edsr ? 0 : G); ++g) {
     float* gout = (float*)(ws + n.o_gf[g & 1]);
     for (int r = 0; r < R; ++r) {
       const int ti = g * R + r;
@@ -398,12 +434,13 @@ struct WgQueue {
     return rc;
   }
   int push(const void* x, const void* dy, int B_, int H_, int W_, float* dw, float* db, int cout_total, int stride,
-           int offset, int acc) {
+           int offset, int acc, float scale = 1.f) {
     if (n && (B_ != B || H_ != H || W_ != W)) RC(flush());
     B = B_; H = H_; W = W_;
     sres_wgrad_job& j = jobs[n++];
     j.x_bf16 = x; j.dy_bf16 = dy; j.dw_oihw = dw; j.dbias = db;
     j.cout_total = cout_total; j.oc_stride = stride; j.oc_offset = offset; j.accumulate = acc;
+    j.scale = scale;
     if (n == SRES_WGRAD_MAX_JOBS) RC(flush());
     return SRES_OK;
   }
@@ -437,7 +474,7 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
   if (ax) for (int i = 0; i < AsyncCtx::kEvents; ++i) ax->live[i] = false;
   float* dres32 = (float*)(ws + n.o_dres32);
   void* dres16 = ws + n.o_dres16;
-  const int xb_last = G * (R + 1);  // bf16 copy of the last group's output = body-tail conv input
+  const int xb_last = n.edsr ? R : G * (R + 1);  // bf16 copy of the body's last output = body-tail conv input
   const bool fused_dot = (H + 1) * (W + 1) >= 128;  // per-tile two-segment partials need an image >= one M tile
 
   for (int seg = seg_begin; seg < seg_end; ++seg) {
@@ -477,6 +514,26 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
       RC(conv64(dres16, WD(n.cidx_bt()), nullptr, B, H, W, st, ga, gb16));
       RC(wq.flush());
       RC(wq.join_all());
+    } else if (seg <= G && n.edsr) {
+      // ResBlocks R-1..0.  ga = fp32 gradient trunk; its bf16 copy for block r lives in gb16 (r = R-1, written by
+      // segment 0) or dt2[r % 3] (written by block r+1's conv1 input-gradient).
+      const bool l2hint = l2_hint_enabled();
+      if (l2hint) RC(sres_l2_persist_window(ga, (size_t)n.lvRows[0] * 256, st));
+      for (int r = R - 1; r >= 0; --r) {
+        float* gr = Gr + n.off_rcab(0, r);
+        const void* g16 = r == R - 1 ? gb16 : (const void*)(ws + n.o_dt2[r % 3]);
+        void* dt1 = ws + n.o_dt1[r % 3];
+        RC(wq.push(T1(r), g16, B, H, W, gr + kConvW + 64, gr + 2 * kConvW + 64, 64, 1, 0, accumulate, n.rs));
+        RC(wq.before_write(dt1));
+        RC(conv64(g16, WD(n.cidx(0, r, 1)), nullptr, B, H, W, st, nullptr, dt1, 0, nullptr, nullptr, nullptr, T1(r)));
+        RC(wq.push(XB(r), dt1, B, H, W, gr, gr + kConvW, 64, 1, 0, accumulate));
+        void* nxt = r > 0 ? (void*)(ws + n.o_dt2[(r - 1) % 3]) : nullptr;
+        if (nxt) RC(wq.before_write(nxt));
+        RC(conv64(dt1, WD(n.cidx(0, r, 0)), nullptr, B, H, W, st, ga, nxt, 0, nullptr, ga));
+      }
+      RC(wq.flush());
+      RC(wq.join_all());
+      if (l2hint) RC(sres_l2_persist_window(nullptr, 0, st));
     } else if (seg <= G) {
       const int g = G - seg;
       const int xb0 = g * (R + 1);  // XB index of the group's input

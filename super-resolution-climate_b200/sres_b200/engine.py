@@ -20,7 +20,11 @@ class RcanDesc(C.Structure):
         ("cin", C.c_int32), ("cout", C.c_int32), ("nfeatures", C.c_int32),
         ("n_groups", C.c_int32), ("n_blocks", C.c_int32), ("reduction", C.c_int32),
         ("n_up", C.c_int32), ("up_factor", C.c_int32 * 4),
+        ("arch", C.c_int32), ("res_scale", C.c_float),
     ]
+
+
+ARCH_RCAN, ARCH_EDSR = 0, 1
 
 
 def upsampler_stages(scale: int) -> List[int]:
@@ -60,13 +64,43 @@ def param_layout(nchannels_in: int, nchannels_out: int, nfeatures: int, nlayers:
     return out
 
 
+def param_layout_edsr(nchannels_in: int, nchannels_out: int, nfeatures: int, nlayers: int, scale: int, kernel_size: int = 3):
+    """Ordered [(state_dict key, shape)] of the reference EDSR (sres/model/edsr/network.py:14-26, ResBlock
+    common/residual.py:41-46, SPUpsample common/upsample.py:44-46) == flat-buffer order."""
+    if kernel_size != 3:
+        raise NotImplementedError("sres_b200 EDSR kernels are specialised for kernel_size == 3")
+    out: List[Tuple[str, Tuple[int, ...]]] = []
+
+    def conv(name, cout, cin, k):
+        out.append((name + ".weight", (cout, cin, k, k)))
+        out.append((name + ".bias", (cout,)))
+
+    Fn = nfeatures
+    conv("head.0", Fn, nchannels_in, 3)
+    for r in range(nlayers):
+        conv(f"body.{r}.body.0", Fn, Fn, 3)
+        conv(f"body.{r}.body.2", Fn, Fn, 3)
+    conv(f"body.{nlayers}", Fn, Fn, 3)
+    for i, f in enumerate(upsampler_stages(scale)):
+        conv(f"tail.0.{2 * i}", f * f * Fn, Fn, 3)
+    conv("tail.1", nchannels_out, Fn, 3)
+    return out
+
+
 class RcanEngine:
     """One RCAN network on one GPU: owns the flat fp32 parameter / gradient buffers and per-shape
     workspaces, and issues the whole forward / backward kernel sequence with one C call each."""
 
     def __init__(self, nchannels_in: int, nchannels_out: int, nfeatures: int, nlayers: int, nblocks: int,
-                 reduction: int, scale: int, device: torch.device):
+                 reduction: int, scale: int, device: torch.device, arch: str = "rcan", res_scale: float = 1.0):
+        """arch 'rcan': nlayers residual groups of nblocks RCABs.  arch 'edsr': ONE group of `nblocks` ResBlocks
+        (pass the reference's EDSR `nlayers` as nblocks and nlayers=1), no channel attention, `res_scale`."""
         device = torch.device(device)
+        if arch not in ("rcan", "edsr"):
+            raise ValueError(f"unknown arch {arch!r}")
+        if arch == "edsr" and nlayers != 1:
+            raise ValueError("EDSR engine: nlayers must be 1 (nblocks = number of ResBlocks)")
+        self.arch, self.res_scale = arch, float(res_scale)
         if device.type != "cuda":
             raise L.SresError(f"sres_b200 RCAN needs a CUDA device (got {device}); there is no CPU fallback")
         self.lib = L.lib()
@@ -74,7 +108,8 @@ class RcanEngine:
         self.cin, self.cout, self.scale = nchannels_in, nchannels_out, scale
         self.nfeatures, self.nlayers, self.nblocks, self.reduction = nfeatures, nlayers, nblocks, reduction
         self.stages = upsampler_stages(scale)
-        self.layout = param_layout(nchannels_in, nchannels_out, nfeatures, nlayers, nblocks, reduction, scale)
+        self.layout = (param_layout(nchannels_in, nchannels_out, nfeatures, nlayers, nblocks, reduction, scale) if arch == "rcan"
+                       else param_layout_edsr(nchannels_in, nchannels_out, nfeatures, nblocks, scale))
         n = sum(int(math.prod(s)) for _, s in self.layout)
         d = self.desc(1, 8, 8)
         self.lib.sres_rcan_param_count.restype = C.c_int64
@@ -112,6 +147,8 @@ class RcanEngine:
         d.n_up = len(self.stages)
         for i, f in enumerate(self.stages):
             d.up_factor[i] = f
+        d.arch = ARCH_EDSR if self.arch == "edsr" else ARCH_RCAN
+        d.res_scale = self.res_scale
         return d
 
     def workspace(self, B: int, H: int, W: int, training: bool) -> torch.Tensor:
@@ -157,9 +194,12 @@ class RcanEngine:
     # -- kernels launched per call (our claim for bench.py's gpu_launches) ----------------------
     def launches_forward(self, H: int, W: int) -> int:
         G, R = self.nlayers, self.nblocks
+        ups = sum(f * f for f in self.stages)
+        if self.arch == "edsr":
+            return 1 + 2 * R + 1 + ups + 1
         fused = (H + 1) * (W + 1) >= 128
         per_rcab = 3 if fused else 4
-        return 1 + G * (R * per_rcab + 1) + 1 + sum(f * f for f in self.stages) + 1
+        return 1 + G * (R * per_rcab + 1) + 1 + ups + 1
 
     def launches_backward(self) -> int:
         """Kernels enqueued by one full backward (weight-gradient jobs go out in batches of <= 4: one
@@ -168,6 +208,8 @@ class RcanEngine:
         ups_dgrad = sum(f * f for f in self.stages)
         seg0_batches = sum(-(-f * f // 4) for f in self.stages) + 1      # per upsampler stage + body-tail conv
         seg0 = 2 + 1 + ups_dgrad + 1 + 2 * seg0_batches                   # tail wgrad(2), tail dgrad, dgrads, bt dgrad
+        if self.arch == "edsr":
+            return seg0 + 2 * R + 2 * (-(-2 * R // 4)) + 2                # 2 dgrads per ResBlock, wgrad batches, head wgrad(2)
         grp_batches = -(-(1 + 2 * R) // 4)
         grp = 1 + R * (1 + 1 + 1) + 2 + 2 * grp_batches                   # gt dgrad, per RCAB ca_bwd + 2 dgrads, ca params(2)
         return seg0 + G * grp + 2

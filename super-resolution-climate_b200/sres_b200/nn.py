@@ -75,30 +75,30 @@ class _RcanFunction(torch.autograd.Function):
         return None, None, None
 
 
-class RCAN(nn.Module):
-    """Drop-in for the reference RCAN (sres/model/rcan/network.py:7-27): same constructor keywords
-    (after hyper-parameter resolution), same parameter names/shapes, `model(x)` takes fp32
-    (B,Cin,h,w) on the CUDA device and returns (B,Cout,h*s,w*s) taking part in autograd."""
+def _resolve_device(device):
+    device = torch.device(device if device is not None else "cuda")
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
 
-    def __init__(self, nchannels_in=1, nchannels_out=1, nfeatures=64, nlayers=10, nblocks=20, cbottleneck=2,
-                 kernel_size=3, bias=True, scale=4, device=None, **unused):
-        super().__init__()
-        if not bias:
-            raise NotImplementedError("sres_b200 RCAN: bias=False is not supported")
-        device = torch.device(device if device is not None else "cuda")
-        if device.type == "cuda" and device.index is None:
-            device = torch.device("cuda", torch.cuda.current_device())
-        self.parms = dict(nchannels_in=nchannels_in, nchannels_out=nchannels_out, nfeatures=nfeatures, nlayers=nlayers,
-                          nblocks=nblocks, cbottleneck=cbottleneck, kernel_size=kernel_size, bias=bias, scale=scale)
-        self.engine = RcanEngine(nchannels_in, nchannels_out, nfeatures, nlayers, nblocks, cbottleneck, scale, device)
+
+class _EngineModule(nn.Module):
+    """Shared plumbing of the engine-backed models: parameters are views into the engine's flat buffer under the
+    reference's state_dict names; forward / backward are single C-ABI calls."""
+
+    engine: RcanEngine
+
+    def _finish_init(self, device):
         self._anchor = torch.zeros(1, device=device, requires_grad=True)
         self._grad_views: Dict[str, torch.Tensor] = {}
         self.ddp = None  # set by enable_data_parallel()
         self._build_tree()
+        names = [k for k, _ in self.named_parameters()]
+        assert names == [k for k, _ in self.engine.layout], "parameter order differs from the reference state_dict order"
+        self._param_list = [p for _, p in self.named_parameters()]
         self.reset_parameters()
 
-    # -- module tree ----------------------------------------------------------------------------
-    def _build_tree(self):
+    def _views(self):
         eng = self.engine
         views, gviews, off = {}, {}, 0
         for name, shape in eng.layout:
@@ -107,37 +107,10 @@ class RCAN(nn.Module):
             gviews[name] = eng.flat_grad[off:off + n].view(shape)
             off += n
         self._grad_views = gviews
+        return views
 
-        def conv(prefix):
-            return _ConvParams(views[prefix + ".weight"], views[prefix + ".bias"])
-
-        G, R = eng.nlayers, eng.nblocks
-        self.head = _seq([(0, conv("head.0"))])
-        groups = []
-        for g in range(G):
-            blocks = []
-            for r in range(R):
-                pre = f"body.{g}.body.{r}.body"
-                ca = _Holder()
-                ca.conv_du = _seq([(0, conv(pre + ".3.conv_du.0")), (1, nn.ReLU(True)), (2, conv(pre + ".3.conv_du.2")),
-                                   (3, nn.Sigmoid())])
-                rcab = _Holder()
-                rcab.body = _seq([(0, conv(pre + ".0")), (1, nn.ReLU(True)), (2, conv(pre + ".2")), (3, ca)])
-                blocks.append((r, rcab))
-            blocks.append((R, conv(f"body.{g}.body.{R}")))
-            grp = _Holder()
-            grp.body = _seq(blocks)
-            groups.append((g, grp))
-        groups.append((G, conv(f"body.{G}")))
-        self.body = _seq(groups)
-        ups = []
-        for i, f in enumerate(eng.stages):
-            ups.append((2 * i, conv(f"tail.0.{2 * i}")))
-            ups.append((2 * i + 1, nn.PixelShuffle(f)))
-        self.tail = _seq([(0, _seq(ups)), (1, conv("tail.1"))])
-        names = [k for k, _ in self.named_parameters()]
-        assert names == [k for k, _ in eng.layout], "parameter order differs from the reference state_dict order"
-        self._param_list = [p for _, p in self.named_parameters()]
+    def _build_tree(self):
+        raise NotImplementedError
 
     def reset_parameters(self):
         """nn.Conv2d's default init (kaiming_uniform(a=sqrt(5)) == U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for
@@ -216,9 +189,104 @@ class RCAN(nn.Module):
         return self
 
 
+class RCAN(_EngineModule):
+    """Drop-in for the reference RCAN (sres/model/rcan/network.py:7-27): same constructor keywords
+    (after hyper-parameter resolution), same parameter names/shapes, `model(x)` takes fp32
+    (B,Cin,h,w) on the CUDA device and returns (B,Cout,h*s,w*s) taking part in autograd."""
+
+    def __init__(self, nchannels_in=1, nchannels_out=1, nfeatures=64, nlayers=10, nblocks=20, cbottleneck=2,
+                 kernel_size=3, bias=True, scale=4, device=None, **unused):
+        super().__init__()
+        if not bias:
+            raise NotImplementedError("sres_b200 RCAN: bias=False is not supported")
+        device = _resolve_device(device)
+        self.parms = dict(nchannels_in=nchannels_in, nchannels_out=nchannels_out, nfeatures=nfeatures, nlayers=nlayers,
+                          nblocks=nblocks, cbottleneck=cbottleneck, kernel_size=kernel_size, bias=bias, scale=scale)
+        self.engine = RcanEngine(nchannels_in, nchannels_out, nfeatures, nlayers, nblocks, cbottleneck, scale, device)
+        self._finish_init(device)
+
+    # -- module tree ----------------------------------------------------------------------------
+    def _build_tree(self):
+        eng = self.engine
+        views = self._views()
+
+        def conv(prefix):
+            return _ConvParams(views[prefix + ".weight"], views[prefix + ".bias"])
+
+        G, R = eng.nlayers, eng.nblocks
+        self.head = _seq([(0, conv("head.0"))])
+        groups = []
+        for g in range(G):
+            blocks = []
+            for r in range(R):
+                pre = f"body.{g}.body.{r}.body"
+                ca = _Holder()
+                ca.conv_du = _seq([(0, conv(pre + ".3.conv_du.0")), (1, nn.ReLU(True)), (2, conv(pre + ".3.conv_du.2")),
+                                   (3, nn.Sigmoid())])
+                rcab = _Holder()
+                rcab.body = _seq([(0, conv(pre + ".0")), (1, nn.ReLU(True)), (2, conv(pre + ".2")), (3, ca)])
+                blocks.append((r, rcab))
+            blocks.append((R, conv(f"body.{g}.body.{R}")))
+            grp = _Holder()
+            grp.body = _seq(blocks)
+            groups.append((g, grp))
+        groups.append((G, conv(f"body.{G}")))
+        self.body = _seq(groups)
+        ups = []
+        for i, f in enumerate(eng.stages):
+            ups.append((2 * i, conv(f"tail.0.{2 * i}")))
+            ups.append((2 * i + 1, nn.PixelShuffle(f)))
+        self.tail = _seq([(0, _seq(ups)), (1, conv("tail.1"))])
+
+
+class EDSR(_EngineModule):
+    """Drop-in for the reference EDSR (sres/model/edsr/network.py:9-32): head conv, `nlayers` ResBlocks
+    (conv, ReLU, conv, *res_scale, +x; common/residual.py:30-54), conv, +head, SPUpsample, conv -- on the same
+    tensor-core convolution kernels as RCAN.  batch_norm=True (never used by the shipped config) is not supported."""
+
+    def __init__(self, nchannels_in=1, nchannels_out=1, nfeatures=64, nlayers=16, kernel_size=3, bias=True, scale=4,
+                 res_scale=1.0, batch_norm=False, device=None, **unused):
+        super().__init__()
+        if not bias or batch_norm:
+            raise NotImplementedError("sres_b200 EDSR: bias=False / batch_norm=True are not supported")
+        device = _resolve_device(device)
+        self.parms = dict(nchannels_in=nchannels_in, nchannels_out=nchannels_out, nfeatures=nfeatures, nlayers=nlayers,
+                          kernel_size=kernel_size, bias=bias, scale=scale, res_scale=res_scale)
+        self.engine = RcanEngine(nchannels_in, nchannels_out, nfeatures, 1, nlayers, 1, scale, device, arch="edsr",
+                                 res_scale=res_scale)
+        self._finish_init(device)
+
+    def _build_tree(self):
+        eng = self.engine
+        views = self._views()
+
+        def conv(prefix):
+            return _ConvParams(views[prefix + ".weight"], views[prefix + ".bias"])
+
+        R = eng.nblocks
+        self.head = _seq([(0, conv("head.0"))])
+        blocks = []
+        for r in range(R):
+            blk = _Holder()
+            blk.body = _seq([(0, conv(f"body.{r}.body.0")), (1, nn.ReLU(True)), (2, conv(f"body.{r}.body.2"))])
+            blocks.append((r, blk))
+        blocks.append((R, conv(f"body.{R}")))
+        self.body = _seq(blocks)
+        ups = []
+        for i, f in enumerate(eng.stages):
+            ups.append((2 * i, conv(f"tail.0.{2 * i}")))
+            ups.append((2 * i + 1, nn.PixelShuffle(f)))
+        self.tail = _seq([(0, _seq(ups)), (1, conv("tail.1"))])
+
+
 def get_model(**config) -> nn.Module:
     """Plugin entry point, same signature as sres/model/rcan/network.py:5-6."""
     return RCAN(**config)
+
+
+def get_edsr_model(**config) -> nn.Module:
+    """Plugin entry point of the EDSR family (sres/model/edsr/network.py:7-8)."""
+    return EDSR(**config)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -305,9 +373,9 @@ class FusedAdam(torch.optim.Optimizer):
     parameter buffer.  Same step()/zero_grad()/state_dict() surface the reference's trainer and
     CheckpointManager use (dual_trainer.py:126,310,323; checkpoints.py:20,44)."""
 
-    def __init__(self, model: RCAN, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
-        if not isinstance(model, RCAN):
-            raise TypeError("FusedAdam(model, ...): pass the sres_b200 RCAN module (it owns the flat buffers)")
+    def __init__(self, model: _EngineModule, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        if not isinstance(model, _EngineModule):
+            raise TypeError("FusedAdam(model, ...): pass the sres_b200 RCAN / EDSR module (it owns the flat buffers)")
         super().__init__(list(model.parameters()), dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.model = model
         eng = model.engine

@@ -12,7 +12,7 @@ import torch
 import rcan_oracle as O
 import tiles_oracle as T
 from gpu_util import rel_l2
-from synth import MODEL_CASES, TILE_CASES, sha, synth_hr, synth_region
+from synth import MODEL_CASES, TILE_CASES, golden_file, sha, synth_hr, synth_region
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-2
@@ -27,6 +27,9 @@ def dev():
 
 def _build(cfg, C, dev_):
     from sres_b200 import nn as snn
+    if O.is_edsr(cfg):
+        return snn.EDSR(nchannels_in=C, nchannels_out=C, nfeatures=64, nlayers=cfg["nlayers"], scale=O.scale_of(cfg),
+                        res_scale=cfg["res_scale"], device=dev_)
     return snn.RCAN(nchannels_in=C, nchannels_out=C, nfeatures=64, nlayers=cfg["nlayers"], nblocks=cfg["nblocks"],
                     cbottleneck=cfg["cbottleneck"], scale=O.scale_of(cfg), device=dev_)
 
@@ -35,7 +38,7 @@ def _build(cfg, C, dev_):
 def test_train_step_matches_oracle_and_golden(name, dev, golden_dir):
     from sres_b200 import nn as snn
     over, B, S, C, loss_name, smooth, full_out = MODEL_CASES[name]
-    gold = np.load(os.path.join(golden_dir, f"rcan_{name}.npz"))
+    gold = np.load(os.path.join(golden_dir, golden_file(name)))
     cfg = O.model_cfg(**over)
     scale = O.scale_of(cfg)
     sd = O.make_state_dict(cfg, C, C)
@@ -297,5 +300,47 @@ def test_controller_api_train_and_infer(dev, tmp_path):
             assert np.isfinite(losses[v]["model"]) and losses[v]["interpolated"] > 0
         res, l2 = tr.evaluate(TSet.Validation, time_index=0)
         assert res["model"].shape[1:] == (2, 48, 48) and np.isfinite(l2["model"])
+    finally:
+        ConfigContext.deactivate()
+
+
+def test_edsr_through_the_controller_and_segments(dev, tmp_path):
+    """EDSR through the mirrored factory / trainer: `model: edsr` picks sres.model.edsr.network,
+    state_dict keys are the reference's, training runs and checkpoints, backward splits into 3 DP segments."""
+    from sres.base.util.config import ConfigContext
+    from sres.controller.workflow import WorkflowController
+    from sres.controller.dual_trainer import TSet
+    from sres_b200 import nn as snn
+    wc = WorkflowController("sres", dict(task="SSS_SST-tiles-48", dataset="synthetic_1200", platform="local"), seed=1)
+    wc.initialize("sres", "edsr", **{
+        "model.nlayers": 3, "model.res_scale": 0.5, "task.batch_size": 8, "task.lr": 2e-4, "task.tile_size": dict(x=12, y=12),
+        "task.tile_order": "corrected", "dataset.region": dict(ys=480, xs=480), "dataset.ntimes": 2,
+        "task.ttsplit": dict(train=0.5, valid=0.5, test=0.0), "platform.results": str(tmp_path)})
+    try:
+        tr = wc.trainer
+        assert type(tr.model).__module__ == "sres.model.edsr.network"
+        cfg_o = O.model_cfg(name="edsr", nlayers=3, res_scale=0.5)
+        assert list(tr.model.state_dict().keys()) == list(O.param_shapes(cfg_o, 2, 2).keys())
+        assert tr.model.engine.num_segments() == 3
+        spans = [tr.model.engine.segment_params(i) for i in range(3)]
+        assert sorted(spans)[0][0] == 0 and sum(c for _, c in spans) == tr.model.engine.n_params
+        out = tr.train(2, True, seed=4456, interp_loss=True, verbose=False)
+        assert np.isfinite(out["prediction"])
+        assert os.path.exists(tr.checkpoint_manager.checkpoint_path(TSet.Train))
+        # segment-wise backward == whole backward
+        m = tr.model
+        x = torch.randn(4, 2, 12, 12, device=dev)
+        tgt = torch.randn(4, 2, 48, 48, device=dev)
+        for p in m.parameters():
+            p.grad = None
+        snn.loss(m(x.clone().requires_grad_(True)), tgt, "l2").backward()
+        whole = m.engine.flat_grad.clone()
+        m.engine.flat_grad.zero_()
+        prd = m(x.clone().requires_grad_(True))
+        pr = prd.detach().requires_grad_(True)
+        snn.loss(pr, tgt, "l2").backward()
+        for seg in range(3):
+            m.engine.backward(x, pr.grad.contiguous(), accumulate=False, seg_begin=seg, seg_end=seg + 1)
+        assert torch.equal(m.engine.flat_grad, whole)
     finally:
         ConfigContext.deactivate()

@@ -9,7 +9,7 @@ import torch
 
 import rcan_oracle as O
 import tiles_oracle as T
-from synth import MODEL_CASES, TILE_CASES, sha, synth_hr, synth_region
+from synth import MODEL_CASES, TILE_CASES, golden_file, sha, synth_hr, synth_region
 
 torch.set_num_threads(8)
 
@@ -17,7 +17,7 @@ torch.set_num_threads(8)
 @pytest.mark.parametrize("name", list(MODEL_CASES))
 def test_rcan_oracle_matches_reference(name, golden_dir):
     over, B, S, C, loss_name, smooth, full_out = MODEL_CASES[name]
-    gold = np.load(os.path.join(golden_dir, f"rcan_{name}.npz"))
+    gold = np.load(os.path.join(golden_dir, golden_file(name)))
     cfg = O.model_cfg(**over)
     scale = O.scale_of(cfg)
     sd = O.make_state_dict(cfg, C, C)
