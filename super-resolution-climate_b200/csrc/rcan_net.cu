@@ -23,6 +23,26 @@
 namespace sres {
 
 constexpr int kConvW = 64 * 64 * 9;  // floats of one 64->64 conv weight
+// bf16 gradient buffers rotate through a ring: a deferred weight-gradient job keeps reading its buffer until its
+// batch (up to 8 jobs = 4 blocks, on the side stream) has RUN, so the ring is two batches deep -- by the time a
+// buffer comes round again the batch that read it was launched >= 4 blocks earlier and the join is free
+constexpr int kRing = 8;
+static int ring_len() {   // buffers actually rotated through (<= kRing): fewer = better L2 locality, more = deeper batches
+  static const int v = [] {
+    const char* e = getenv("SRES_RING");
+    int n = e ? atoi(e) : 3;
+    return n < 3 ? 3 : (n > kRing ? kRing : n);
+  }();
+  return v;
+}
+static int wgrad_batch_jobs() {
+  static const int v = [] {
+    const char* e = getenv("SRES_WGRAD_BATCH");
+    int n = e ? atoi(e) : 4;  // measured on B200: 4 jobs / ring 3 == 8 jobs / ring 5 within noise (28.9-29.4 ms); deeper rings lose L2 locality
+    return n < 1 ? 1 : (n > SRES_WGRAD_MAX_JOBS ? SRES_WGRAD_MAX_JOBS : n);
+  }();
+  return v;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Optional in-situ profiler (SRES_PROFILE=1, eager mode only): CUDA events around every enqueued
@@ -74,7 +94,7 @@ struct Net {
   size_t o_xb, o_t1, o_t2, o_mean, o_s, o_ds, o_resb, o_u[4];
   size_t o_hf, o_gf[2], o_xf, o_pool_part, o_pool_sum;
   size_t o_sbias;  // EDSR: res_scale * bias of every ResBlock's second conv
-  size_t o_ga, o_gb32, o_gb16, o_dt2[3], o_dt1[3], o_ds_part, o_wg_ws, o_sw_ws, o_ca_scr, o_du16[4], o_du32[4], o_dres32, o_dres16;
+  size_t o_ga, o_gb32, o_gb16, o_dt2[kRing], o_dt1[kRing], o_ds_part, o_wg_ws, o_sw_ws, o_ca_scr, o_du16[4], o_du32[4], o_dres32, o_dres16;
   size_t total;
   int n_xb, n_t;  // saved-buffer counts (1 in inference mode)
   long long cidx(int g, int r, int which) const { return (long long)g * per + 2 * r + which; }
@@ -169,8 +189,7 @@ static int build_net(Net* n, const sres_rcan_desc* d, int training) {
   if (training) {
     n->o_ga = take(f32);
     n->o_gb16 = take(bf);
-    // rings of 3: the deferred weight-gradient jobs still read a buffer while the next two are produced
-    for (int k = 0; k < 3; ++k) { n->o_dt2[k] = take(bf); n->o_dt1[k] = take(bf); }
+    for (int k = 0; k < kRing; ++k) { n->o_dt2[k] = take(bf); n->o_dt1[k] = take(bf); }
     if (!edsr) {
       n->o_ds = take((size_t)n->n_t * d->B * 64 * 4);
       n->o_gb32 = take(f32);
@@ -441,7 +460,7 @@ struct WgQueue {
     j.x_bf16 = x; j.dy_bf16 = dy; j.dw_oihw = dw; j.dbias = db;
     j.cout_total = cout_total; j.oc_stride = stride; j.oc_offset = offset; j.accumulate = acc;
     j.scale = scale;
-    if (n == SRES_WGRAD_MAX_JOBS) RC(flush());
+    if (n == wgrad_batch_jobs()) RC(flush());
     return SRES_OK;
   }
   // call before enqueuing a kernel that writes `buf`
@@ -516,18 +535,18 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
       RC(wq.join_all());
     } else if (seg <= G && n.edsr) {
       // ResBlocks R-1..0.  ga = fp32 gradient trunk; its bf16 copy for block r lives in gb16 (r = R-1, written by
-      // segment 0) or dt2[r % 3] (written by block r+1's conv1 input-gradient).
+      // segment 0) or dt2[r % ring_len()] (written by block r+1's conv1 input-gradient).
       const bool l2hint = l2_hint_enabled();
       if (l2hint) RC(sres_l2_persist_window(ga, (size_t)n.lvRows[0] * 256, st));
       for (int r = R - 1; r >= 0; --r) {
         float* gr = Gr + n.off_rcab(0, r);
-        const void* g16 = r == R - 1 ? gb16 : (const void*)(ws + n.o_dt2[r % 3]);
-        void* dt1 = ws + n.o_dt1[r % 3];
+        const void* g16 = r == R - 1 ? gb16 : (const void*)(ws + n.o_dt2[r % ring_len()]);
+        void* dt1 = ws + n.o_dt1[r % ring_len()];
         RC(wq.push(T1(r), g16, B, H, W, gr + kConvW + 64, gr + 2 * kConvW + 64, 64, 1, 0, accumulate, n.rs));
         RC(wq.before_write(dt1));
         RC(conv64(g16, WD(n.cidx(0, r, 1)), nullptr, B, H, W, st, nullptr, dt1, 0, nullptr, nullptr, nullptr, T1(r)));
         RC(wq.push(XB(r), dt1, B, H, W, gr, gr + kConvW, 64, 1, 0, accumulate));
-        void* nxt = r > 0 ? (void*)(ws + n.o_dt2[(r - 1) % 3]) : nullptr;
+        void* nxt = r > 0 ? (void*)(ws + n.o_dt2[(r - 1) % ring_len()]) : nullptr;
         if (nxt) RC(wq.before_write(nxt));
         RC(conv64(dt1, WD(n.cidx(0, r, 0)), nullptr, B, H, W, st, ga, nxt, 0, nullptr, ga));
       }
@@ -555,8 +574,8 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
         const float* b2 = w2 + 64 * n.hid;
         const float* mean = (const float*)(ws + n.o_mean) + (size_t)ti * B * 64;
         float* dsv = (float*)(ws + n.o_ds) + (size_t)ti * B * 64;
-        void* dt2 = ws + n.o_dt2[ti % 3];
-        void* dt1 = ws + n.o_dt1[ti % 3];
+        void* dt2 = ws + n.o_dt2[ti % ring_len()];
+        void* dt1 = ws + n.o_dt1[ti % ring_len()];
         RC(wq.before_write(dt2));
         { PROF("ca_bwd");
         if (fused_dot) RC(sres_ca_bwd_apply(gb32, dot_part, w1, b1, w2, b2, n.hid, mean, dt2, dsv, B, H, W, st));

@@ -202,15 +202,18 @@ class RcanEngine:
         return 1 + G * (R * per_rcab + 1) + 1 + ups + 1
 
     def launches_backward(self) -> int:
-        """Kernels enqueued by one full backward (weight-gradient jobs go out in batches of <= 4: one
-        tensor-core kernel + one reduce kernel per batch)."""
+        """Kernels enqueued by one full backward (weight-gradient jobs of one geometry go out in batches of up to
+        SRES_WGRAD_BATCH (default 4, at most 8): one tensor-core kernel + one reduce kernel per batch)."""
         G, R = self.nlayers, self.nblocks
+        J = min(8, max(1, int(os.environ.get("SRES_WGRAD_BATCH", "4"))))
         ups_dgrad = sum(f * f for f in self.stages)
-        seg0_batches = sum(-(-f * f // 4) for f in self.stages) + 1      # per upsampler stage + body-tail conv
+        # segment 0: the up-conv jobs of stage i run at level-i geometry; the body-tail job joins the level-0 batch
+        jobs0 = (self.stages[0] ** 2 if self.stages else 0) + 1
+        seg0_batches = sum(-(-f * f // J) for f in self.stages[1:]) + -(-jobs0 // J)
         seg0 = 2 + 1 + ups_dgrad + 1 + 2 * seg0_batches                   # tail wgrad(2), tail dgrad, dgrads, bt dgrad
         if self.arch == "edsr":
-            return seg0 + 2 * R + 2 * (-(-2 * R // 4)) + 2                # 2 dgrads per ResBlock, wgrad batches, head wgrad(2)
-        grp_batches = -(-(1 + 2 * R) // 4)
+            return seg0 + 2 * R + 2 * (-(-2 * R // J)) + 2                # 2 dgrads per ResBlock, wgrad batches, head wgrad(2)
+        grp_batches = -(-(1 + 2 * R) // J)
         grp = 1 + R * (1 + 1 + 1) + 2 + 2 * grp_batches                   # gt dgrad, per RCAB ca_bwd + 2 dgrads, ca params(2)
         return seg0 + G * grp + 2
 
