@@ -26,6 +26,7 @@ from sres.data.tiles import TileIterator
 from sres.model.manager import SRModels
 from sres_b200 import _lib as L
 from sres_b200 import nn as _snn
+from sres_b200.parallel import gather_rows, shard_range
 
 TensorOrTensors = Union[Tensor, Sequence[Tensor]]
 
@@ -242,8 +243,12 @@ class ModelTrainer(object):
         output_vars = [cvar] if cvar is not None else vnames
         batch_model_losses, batch_interp_losses, batches = [], [], []
         tile_iter = TileIterator.get_iterator(ntiles=timeslice.sizes["tiles"])
+        ctiles = list(iter(tile_iter))
+        # data parallel: rank r runs the forward on a contiguous range of the tile batches; the products are gathered
+        # so every rank (rank 0 in practice) can stitch the full image
+        lo, hi = shard_range(len(ctiles), self.rank, self.world) if self.world > 1 else (0, len(ctiles))
         with torch.no_grad():
-            for ctile in iter(tile_iter):
+            for ctile in ctiles[lo:hi]:
                 batch_data = self.get_srbatch(ctile, ctime, shuffle=False)
                 if batch_data is None:
                     break
@@ -254,6 +259,24 @@ class ModelTrainer(object):
                 a = batch_data.attrs
                 batches.append(dict(input=denorm(binput, a), target=denorm(btarget, a), interpolated=denorm(binterp, a),
                                     model=denorm(boutput, a)))
+        if self.world > 1:
+            ntiles = int(timeslice.sizes["tiles"])
+            counts = []   # tile rows per rank (equal batch sizes except the last batch)
+            for r in range(self.world):
+                rlo, rhi = shard_range(len(ctiles), r, self.world)
+                counts.append(sum(min(c["end"], ntiles) - c["start"] for c in ctiles[rlo:rhi]))
+            nch, hr = len(self.target_variables), int(timeslice.shape[2])
+            scale = int(np.prod(cfg().model.downscale_factors)) * int(cfg().task.get("data_downsample", 1.0))
+            merged = {}
+            for k in ("input", "target", "interpolated", "model"):
+                side = hr // scale if k == "input" else hr // int(cfg().task.get("data_downsample", 1.0))
+                local = torch.cat([torch.as_tensor(bd[k], device=self.device).float() for bd in batches], dim=0) if batches else None
+                merged[k] = gather_rows(local, counts, (nch, side, side), self.device)
+            batches = [merged]
+            stat = torch.tensor([float(np.sum(batch_model_losses)), float(np.sum(batch_interp_losses)), float(len(batch_model_losses))],
+                                dtype=torch.float64, device=self.device)
+            dist.all_reduce(stat)
+            batch_model_losses, batch_interp_losses = [float(stat[0] / stat[2])], [float(stat[1] / stat[2])]
         images, losses = {}, {}
         for ivar, vname in enumerate(output_vars):
             images[vname] = self.assemble_images(batches, ivar, timeslice.coords["tiles"], timeslice.attrs["grid_shape"])

@@ -5,7 +5,7 @@ Not in the reference (single process, single device: sres/base/gpu.py:6-15); SUR
 Tiles are independent units (no inter-tile halo, no BatchNorm), weights and optimizer state are
 replicated, the only exchange per step is the gradient sum (+ one scalar for the RMSE loss).
 """
-from typing import Optional
+from typing import Optional, Sequence
 
 import torch
 import torch.distributed as dist
@@ -16,6 +16,32 @@ def shard_range(n_items: int, rank: int, world: int):
     base, rem = divmod(n_items, world)
     start = rank * base + min(rank, rem)
     return start, start + base + (1 if rank < rem else 0)
+
+
+def gather_rows(local: Optional[torch.Tensor], counts: Sequence[int], row_shape: Sequence[int], device, group=None) -> torch.Tensor:
+    """Concatenate per-rank row blocks in rank order on every rank: rank r contributes `counts[r]` rows of shape
+    `row_shape` (fp32; `local` may be None / empty when counts[rank] == 0).  One all_gather of blocks padded to the
+    longest.  Inference sharding: ranks run the forward on contiguous tile ranges, the gathered
+    products are stitched on rank 0."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if len(counts) != world:
+        raise ValueError("gather_rows: one count per rank")
+    n_local = 0 if local is None else int(local.shape[0])
+    if n_local != counts[rank]:
+        raise ValueError(f"gather_rows: rank {rank} holds {n_local} rows, expected {counts[rank]}")
+    pad = torch.zeros((max(counts),) + tuple(row_shape), dtype=torch.float32, device=device)
+    if n_local:
+        pad[:n_local] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p[:n] for p, n in zip(parts, counts)], dim=0)
+
+
+def gather_ranges(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """Inverse of `shard_range` for an (n_total, ...) tensor."""
+    world = dist.get_world_size(group)
+    counts = [e - s for s, e in (shard_range(n_total, r, world) for r in range(world))]
+    return gather_rows(local, counts, local.shape[1:], local.device, group)
 
 
 class SegmentAllReduce:

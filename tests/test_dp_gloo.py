@@ -50,7 +50,7 @@ def _worker(rank, world, port, out_q):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from sres_b200.parallel import SegmentAllReduce, shard_range
+        from sres_b200.parallel import SegmentAllReduce, gather_ranges, gather_rows, shard_range
         eng = _StubEngine(rank)
         ddp = SegmentAllReduce(eng, None, average=False)
         ddp.backward(eng, None, None, accumulate=False)
@@ -75,7 +75,16 @@ def _worker(rank, world, port, out_q):
         dist.all_gather_object(gathered, mine)
         flat = sorted(b for part in gathered for b in part)
         ok_shard = flat == batches[: len(batches) - len(batches) % world] and len(set(map(len, gathered))) == 1
-        out_q.put((rank, ok_sum, ok_loss, ok_shard))
+        # inference sharding: ranks hold contiguous tile ranges (uneven, one rank may be empty), gather restores tile order
+        tiles = torch.arange(7 * 2 * 3 * 3, dtype=torch.float32).reshape(7, 2, 3, 3)
+        s7, e7 = shard_range(7, rank, world)
+        ok_gather = bool(torch.equal(gather_ranges(tiles[s7:e7], 7), tiles))
+        counts = [5, 0] if world == 2 else [5] + [0] * (world - 1)
+        local = tiles[:5] if rank == 0 else None
+        ok_gather = ok_gather and bool(torch.equal(gather_rows(local, counts, (2, 3, 3), torch.device("cpu")), tiles[:5]))
+        with pytest.raises(ValueError):
+            gather_rows(tiles[:1], counts if rank else [4] + counts[1:], (2, 3, 3), torch.device("cpu"))
+        out_q.put((rank, ok_sum, ok_loss, ok_shard and ok_gather))
     finally:
         dist.destroy_process_group()
 

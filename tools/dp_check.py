@@ -36,6 +36,27 @@ same = torch.tensor([float((gd - gr).abs().max())], device=dev)
 allg = [torch.zeros_like(gd) for _ in range(world)]
 dist.all_gather(allg, gd)
 ident = all(torch.equal(allg[0], a) for a in allg)
+# ---- sharded inference through the mirrored trainer: DP-N stitched images == single-GPU stitched images ----------
+import numpy as np, tempfile
+from sres.base.util.config import ConfigContext
+from sres.controller.workflow import WorkflowController
+from sres.controller.config import ResultStructure, TSet
+tmp = tempfile.mkdtemp()
+over = {"model.nlayers": 2, "model.nblocks": 2, "task.batch_size": 8, "task.tile_size": dict(x=12, y=12), "task.tile_order": "corrected",
+        "dataset.region": dict(ys=480, xs=576), "dataset.ntimes": 2, "platform.results": tmp}
+wc = WorkflowController("sres", dict(task="SSS_SST-tiles-48", dataset="synthetic_1200", platform="local"), seed=1)
+wc.initialize("sres", "rcan-10-20-64", **over)
+tr = wc.trainer
+dist.broadcast(tr.model.engine.flat, src=0); tr.model.engine.mark_params_changed()
+images, losses = wc.inference(0, ResultStructure.Image)
+tr.world, tr.rank = 1, 0           # the same trainer, unsharded
+images1, losses1 = tr.process_image(TSet.Validation, 0, interp_loss=True)
+same_img = all(np.array_equal(images[v][k], images1[v][k], equal_nan=True) for v in images for k in images[v])
+same_loss = all(abs(losses[v]["model"] - losses1[v]["model"]) < 1e-6 for v in losses)
+ConfigContext.deactivate()
+if rank == 0:
+    print(f"RESULT dp{world} inference: stitched images identical to unsharded = {same_img}; losses equal = {same_loss}")
+    assert same_img and same_loss
 if rank == 0:
     print(f"RESULT dp{world}: loss {loss.item():.7f} vs single-GPU {loss_r.item():.7f}; grad rel-L2 vs single-GPU = {rel:.3e}; identical across ranks = {ident}")
     assert abs(loss.item() - loss_r.item()) < 1e-6 and rel < 1e-5 and ident
