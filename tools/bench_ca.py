@@ -4,7 +4,8 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, os.path.join(ROOT, "super-resolution-climate_b200"))
 from sres_b200 import _lib as L
 lib = L.lib(); dev = torch.device("cuda:0")
-B, H, W, hid = 64, 48, 48, 4
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+H, W, hid = 48, 48, 4
 rows = B * 49 * 49
 nt = lib.sres_conv_mtiles(B, H, W)
 NB = 12
@@ -26,5 +27,5 @@ def timeit(fn, rot, n=48):
     for i in range(n): fn(i % NB if rot else 0)
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / n * 1e3
-print(f"bpi={bpi}  ca_apply_fwd: cold {timeit(fwd, True):.1f} us, hot {timeit(fwd, False):.1f} us   (118 MB)")
+print(f"bpi={bpi}  ca_apply_fwd: cold {timeit(fwd, True):.1f} us, hot {timeit(fwd, False):.1f} us   (118 MB at B=64); B={B}, {118e6*B/64/timeit(fwd, False)/1e6:.2f} TB/s hot")
 print(f"bpi={bpi}  ca_bwd (2 kernels): cold {timeit(bwd, True):.1f} us, hot {timeit(bwd, False):.1f} us   (2 x 59 MB)")
