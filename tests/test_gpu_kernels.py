@@ -186,8 +186,10 @@ def test_upsampler_conv_pixelshuffle_and_back(env, f):
         assert torch.equal(got, un[:, :, sub])
 
 
+@pytest.mark.parametrize("n128", ["0", "1"])
 @pytest.mark.parametrize("B,H,W", GEOMS[:4])
-def test_conv_wgrad(env, B, H, W):
+def test_conv_wgrad(env, B, H, W, n128, monkeypatch):
+    monkeypatch.setenv("SRES_WGRAD_N128", n128)   # plain two-taps-per-MMA scheme and the opt-in four-taps one
     L, lib, dev = env
     lib.sres_conv_wgrad_workspace_bytes.restype = C.c_size_t
     x = bf16_round(torch.randn(B, 64, H, W))
