@@ -73,6 +73,9 @@ class ModelTrainer(object):
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         if self.world > 1:
             self.model.enable_data_parallel()
+            # every rank starts from rank 0's weights (constructors draw from per-process RNG state)
+            dist.broadcast(self.model.engine.flat, src=0)
+            self.model.engine.mark_params_changed()
         self.input, self.target, self.product, self.interp = {}, {}, {}, {}
         self.current_losses: Dict[str, float] = {}
         self.time_index: int = -1
@@ -82,6 +85,15 @@ class ModelTrainer(object):
         self.train_state = None
 
     # -- plumbing ----------------------------------------------------------------------------------
+    def _sync_python_rng(self):
+        """Data parallel only: the timeslice order, the tile-batch shuffle and the flip index are drawn from Python's
+        `random` (like the reference); all ranks must draw the same ones or they would walk different timeslices and
+        issue different numbers of collectives.  Rank 0's next draw seeds everybody."""
+        if self.world > 1:
+            s = torch.tensor([random.getrandbits(62)], dtype=torch.int64, device=self.device)
+            dist.broadcast(s, src=0)
+            random.seed(int(s.item()))
+
     def get_dataset(self) -> BatchDataset:
         return self.model_manager.get_dataset()
 
@@ -172,6 +184,7 @@ class ModelTrainer(object):
             itime0 = self.train_state.get("itime", 0)
             epoch_loss = self.train_state.get("loss", float("inf"))
             nepochs += epoch0
+        self._sync_python_rng()
         self.init_data_timestamps()
         for epoch in range(epoch0, nepochs):
             self.model.train()
@@ -234,6 +247,7 @@ class ModelTrainer(object):
                 print("Error loading checkpoint file, skipping evaluation.")
                 return {}, {}
         self.time_index = itime
+        self._sync_python_rng()
         self.init_data_timestamps()
         ctime = kwargs.get("ctime", None)
         if ctime is None:
@@ -310,6 +324,7 @@ class ModelTrainer(object):
         Returns (dict(input,target,model,interpolated) -> numpy (N,C,·,·), dict(model, interpolated))."""
         assert tset in [TSet.Validation, TSet.Test], f"Invalid tset in training evaluation: {tset.name}"
         self.time_index = kwargs.get("time_index", self.time_index)
+        self._sync_python_rng()
         self.init_data_timestamps()
         ml, il, res = [], [], dict(input=[], target=[], model=[], interpolated=[])
         with torch.no_grad():

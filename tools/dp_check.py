@@ -53,7 +53,17 @@ tr.world, tr.rank = 1, 0           # the same trainer, unsharded
 images1, losses1 = tr.process_image(TSet.Validation, 0, interp_loss=True)
 same_img = all(np.array_equal(images[v][k], images1[v][k], equal_nan=True) for v in images for k in images[v])
 same_loss = all(abs(losses[v]["model"] - losses1[v]["model"]) < 1e-6 for v in losses)
+# ---- data-parallel training through the trainer loop: same shuffles on every rank, replicas stay identical ----------
+tr.world, tr.rank = world, rank
+out = tr.train(2, True, seed=5, verbose=False)   # range(1, nepochs): one epoch, like the reference
+flat = tr.model.engine.flat
+allw = [torch.zeros_like(flat) for _ in range(world)]
+dist.all_gather(allw, flat)
+same_w = all(torch.equal(allw[0], a) for a in allw) and bool(torch.isfinite(flat).all())
 ConfigContext.deactivate()
+if rank == 0:
+    print(f"RESULT dp{world} trainer.train: loss {out['prediction']:.5f}; replicas identical after training = {same_w}")
+    assert same_w
 if rank == 0:
     print(f"RESULT dp{world} inference: stitched images identical to unsharded = {same_img}; losses equal = {same_loss}")
     assert same_img and same_loss
