@@ -20,6 +20,8 @@ dsp = torch.empty(B * bpi * 64, device=dev)
 st = L.cur_stream()
 def fwd(i): return lib.sres_ca_apply_fwd(L.ptr(t2[i]), L.ptr(pool), None, L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2), hid, L.ptr(x[i]), L.ptr(x[i]), L.ptr(xb[i]), L.ptr(mean), L.ptr(sv), B, H, W, st)
 def bwd(i): return lib.sres_ca_bwd(L.ptr(x[i]), L.ptr(t2[i]), L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2), hid, L.ptr(mean), L.ptr(dsp), L.ptr(xb[i]), L.ptr(ds), B, H, W, st)
+lib.sres_ca_bwd_apply.restype = C.c_int
+def bwd_apply(i): return lib.sres_ca_bwd_apply(L.ptr(x[i]), L.ptr(pool), L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2), hid, L.ptr(mean), L.ptr(xb[i]), L.ptr(ds), B, H, W, st)
 def timeit(fn, rot, n=48):
     for i in range(6): L.check(fn(i % NB if rot else 0), "k")
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -29,3 +31,4 @@ def timeit(fn, rot, n=48):
     return a.elapsed_time(b) / n * 1e3
 print(f"bpi={bpi}  ca_apply_fwd: cold {timeit(fwd, True):.1f} us, hot {timeit(fwd, False):.1f} us   (118 MB at B=64); B={B}, {118e6*B/64/timeit(fwd, False)/1e6:.2f} TB/s hot")
 print(f"bpi={bpi}  ca_bwd (2 kernels): cold {timeit(bwd, True):.1f} us, hot {timeit(bwd, False):.1f} us   (2 x 59 MB)")
+print(f"bpi={bpi}  ca_bwd_apply (fused-dot path, in-network kernel): cold {timeit(bwd_apply, True):.1f} us, hot {timeit(bwd_apply, False):.1f} us   (59 MB at B=64)")
