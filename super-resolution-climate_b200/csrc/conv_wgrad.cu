@@ -387,7 +387,11 @@ extern "C" int sres_conv3x3_wgrad_batch(const sres_wgrad_job* jobs, int njobs, i
            : launch_pdl(conv3x3_wgrad_kernel<false>, dim3(grid), dim3(256), smem, stream, maps, tmPart, p);
   if (e != cudaSuccess) return set_cuda_error(e, "wgrad: launch");
   const int total = kWgPartFloats + 64;
-  e = launch_pdl(wgrad_reduce_kernel, dim3((total + 255) / 256, njobs), dim3(256), 0, stream, (const float*)part,
+  // The reduce kernel is launched WITHOUT programmatic dependent launch: as a PDL secondary replayed from a CUDA graph
+  // it occasionally summed a bias-gradient partial of the split-K kernel that was not the final one (one conv bias off
+  // by ~0.5 % in about a third of full-size backward passes; never in eager mode, never for the TMA-stored weight
+  // partials; tests/test_gpu_model.py::test_full_size_properties).  A full dependency costs ~1 us per batch.
+  e = launch_pdl_if(false, wgrad_reduce_kernel, dim3((total + 255) / 256, njobs), dim3(256), 0, stream, (const float*)part,
                  (const float*)p.part_bias, p.max_split, rj);
   if (e != cudaSuccess) return set_cuda_error(e, "wgrad: reduce launch");
   return SRES_OK;
