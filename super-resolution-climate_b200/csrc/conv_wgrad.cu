@@ -184,6 +184,11 @@ conv3x3_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
         acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
         acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
       }
+      // The arrive hands the slot back to the TMA producer (async proxy).  These generic-proxy loads must be ordered
+      // before it by a PROXY fence: without it ptxas schedules the arrive ahead of the last loads' consumers, and under
+      // load-store pressure from co-resident kernels the refill overtook a load (one conv-bias gradient off by ~0.5 % in
+      // a fraction of the backward passes; tests/test_gpu_model.py::test_full_size_properties).
+      fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_empty[slot]);
     }
@@ -387,11 +392,7 @@ extern "C" int sres_conv3x3_wgrad_batch(const sres_wgrad_job* jobs, int njobs, i
            : launch_pdl(conv3x3_wgrad_kernel<false>, dim3(grid), dim3(256), smem, stream, maps, tmPart, p);
   if (e != cudaSuccess) return set_cuda_error(e, "wgrad: launch");
   const int total = kWgPartFloats + 64;
-  // The reduce kernel is launched WITHOUT programmatic dependent launch: as a PDL secondary replayed from a CUDA graph
-  // it occasionally summed a bias-gradient partial of the split-K kernel that was not the final one (one conv bias off
-  // by ~0.5 % in about a third of full-size backward passes; never in eager mode, never for the TMA-stored weight
-  // partials; tests/test_gpu_model.py::test_full_size_properties).  A full dependency costs ~1 us per batch.
-  e = launch_pdl_if(false, wgrad_reduce_kernel, dim3((total + 255) / 256, njobs), dim3(256), 0, stream, (const float*)part,
+  e = launch_pdl(wgrad_reduce_kernel, dim3((total + 255) / 256, njobs), dim3(256), 0, stream, (const float*)part,
                  (const float*)p.part_bias, p.max_split, rj);
   if (e != cudaSuccess) return set_cuda_error(e, "wgrad: reduce launch");
   return SRES_OK;
