@@ -160,6 +160,85 @@ small_in_wgrad_kernel(const float* __restrict__ g1, const float* __restrict__ g2
   }
 }
 
+// Band-tiled head-conv weight gradient for W % 4 == 0 (the mirror image of small_out_wgrad_kernel below): the planar
+// input band (+halo) sits in shared memory, a thread owns 2 features of the fp32 gradient rows (g1 + g2), a warp walks
+// groups of four consecutive positions and reads the 6 inputs of a 3-tap row with three 8-byte shared loads.  The
+// scalar kernel above keeps its loads under boundary branches and was latency-bound (208 us for 78 MB).
+template <int CS>
+__global__ void __launch_bounds__(256)
+small_in_wgrad_band_kernel(const float* __restrict__ g1, const float* __restrict__ g2, const float* __restrict__ in, int B,
+                           int H, int W, float* __restrict__ part) {
+  extern __shared__ float s_x[];  // [CS][kBandRows+2][SW], then the cross-warp reduction buffer
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int n0 = lane * 2;
+  const int P = W + 1, RP = (H + 1) * P, SW = (W + 3) & ~1;
+  float acc[2][CS * 9], accb[2] = {0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < CS * 9; ++i) acc[j][i] = 0.f;
+  const int bands = (H + kBandRows - 1) / kBandRows;
+  const int gpr = W >> 2;
+  for (int item = blockIdx.x; item < B * bands; item += gridDim.x) {
+    const int b = item / bands, y0 = (item % bands) * kBandRows;
+    __syncthreads();
+    for (int i = threadIdx.x; i < CS * (kBandRows + 2) * SW; i += blockDim.x) {
+      const int xx = i % SW - 1, yy = (i / SW) % (kBandRows + 2) + y0 - 1, c = i / (SW * (kBandRows + 2));
+      s_x[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(in + (((size_t)b * CS + c) * H + yy) * W + xx) : 0.f;
+    }
+    __syncthreads();
+    const int rows = min(kBandRows, H - y0);
+    for (int grp = wrp; grp < rows * gpr; grp += 8) {
+      const int yl = grp / gpr, x0 = (grp - yl * gpr) * 4;
+      const size_t q = (size_t)b * RP + (size_t)(y0 + yl) * P + x0;
+      float u0[4], u1[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 gv = *reinterpret_cast<const float2*>(g1 + (q + j) * 64 + n0);
+        if (g2) {
+          const float2 g2v = *reinterpret_cast<const float2*>(g2 + (q + j) * 64 + n0);
+          gv.x += g2v.x; gv.y += g2v.y;
+        }
+        u0[j] = gv.x; u1[j] = gv.y;
+        accb[0] += gv.x; accb[1] += gv.y;
+      }
+#pragma unroll
+      for (int c = 0; c < CS; ++c)
+#pragma unroll
+        for (int ty = 0; ty < 3; ++ty) {   // tap (ty, tx) reads the input at (y + ty - 1, x + tx - 1) = smem (yl + ty, x + tx)
+          const float* dr = s_x + (c * (kBandRows + 2) + yl + ty) * SW + x0;
+          const float2 d01 = *reinterpret_cast<const float2*>(dr);
+          const float2 d23 = *reinterpret_cast<const float2*>(dr + 2);
+          const float2 d45 = *reinterpret_cast<const float2*>(dr + 4);
+          const float d6[6] = {d01.x, d01.y, d23.x, d23.y, d45.x, d45.y};
+#pragma unroll
+          for (int tx = 0; tx < 3; ++tx)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              acc[0][c * 9 + ty * 3 + tx] = fmaf(u0[j], d6[j + tx], acc[0][c * 9 + ty * 3 + tx]);
+              acc[1][c * 9 + ty * 3 + tx] = fmaf(u1[j], d6[j + tx], acc[1][c * 9 + ty * 3 + tx]);
+            }
+        }
+    }
+  }
+  __syncthreads();
+  float* red = s_x;  // [8 warps][64 n][kSwAcc]
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+#pragma unroll
+    for (int i = 0; i < CS * 9; ++i) red[(wrp * 64 + n0 + j) * kSwAcc + i] = acc[j][i];
+    for (int i = CS * 9; i < kSwAcc - 1; ++i) red[(wrp * 64 + n0 + j) * kSwAcc + i] = 0.f;
+    red[(wrp * 64 + n0 + j) * kSwAcc + kSwAcc - 1] = accb[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * kSwAcc; i += 256) {
+    float sum = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) sum += red[ww * 64 * kSwAcc + i];
+    part[(size_t)blockIdx.x * 64 * kSwAcc + i] = sum;
+  }
+}
+
 __global__ void small_in_wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int Cs,
                                              float* __restrict__ dw, float* __restrict__ db, int accumulate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -398,7 +477,27 @@ extern "C" int sres_small_in_wgrad(const float* g1_f32, const float* g2_f32, con
   const int grid = small_grid();
   if (workspace_bytes < (size_t)grid * 64 * kSwAcc * sizeof(float))
     return set_error(SRES_ERR_INVALID_ARG, "small_in_wgrad: workspace too small");
-  small_in_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g1_f32, g2_f32, in_nchw, B, Cs, H, W, (float*)workspace);
+  size_t smem = (size_t)Cs * (kBandRows + 2) * ((W + 3) & ~1) * sizeof(float);
+  const size_t red = (size_t)8 * 64 * kSwAcc * sizeof(float);
+  if (smem < red) smem = red;
+  if ((W & 3) == 0 && smem <= 200 * 1024) {
+    cudaStream_t st = (cudaStream_t)stream;
+    float* partp = (float*)workspace;
+#define SRES_LAUNCH_HEAD_WG(CS)                                                                                       \
+  do {                                                                                                                \
+    cudaFuncSetAttribute(small_in_wgrad_band_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    small_in_wgrad_band_kernel<CS><<<grid, 256, smem, st>>>(g1_f32, g2_f32, in_nchw, B, H, W, partp);                  \
+  } while (0)
+    switch (Cs) {
+      case 1: SRES_LAUNCH_HEAD_WG(1); break;
+      case 2: SRES_LAUNCH_HEAD_WG(2); break;
+      case 3: SRES_LAUNCH_HEAD_WG(3); break;
+      default: SRES_LAUNCH_HEAD_WG(4); break;
+    }
+#undef SRES_LAUNCH_HEAD_WG
+  } else {
+    small_in_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g1_f32, g2_f32, in_nchw, B, Cs, H, W, (float*)workspace);
+  }
   SRES_CHECK_LAUNCH("small_in_wgrad: launch");
   small_in_wgrad_reduce_kernel<<<(64 * kSwAcc + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, grid,
                                                                                             Cs, dw, db, accumulate);
