@@ -71,6 +71,37 @@ def test_param_count_and_segments(lib):
     assert lib.sres_rcan_workspace_bytes(C.byref(d), 1, C.byref(ws)) == 0 and ws.value > 0
 
 
+def test_edsr_param_layout_and_segments(lib):
+    """EDSR through the same C entry points (arch flag): parameter count / order equal the reference's state_dict
+    (via the oracle's restatement), three backward segments partition the flat buffer, bad descriptions are refused."""
+    from sres_b200.engine import ARCH_EDSR, RcanDesc, param_layout_edsr
+    import rcan_oracle as O
+    d = RcanDesc()
+    d.B, d.H, d.W, d.cin, d.cout, d.nfeatures, d.n_groups, d.n_blocks, d.reduction, d.n_up = 4, 48, 48, 2, 2, 64, 1, 16, 1, 2
+    d.up_factor[0] = d.up_factor[1] = 2
+    d.arch, d.res_scale = ARCH_EDSR, 1.0
+    lib.sres_rcan_param_count.restype = C.c_int64
+    n = lib.sres_rcan_param_count(C.byref(d))
+    layout = param_layout_edsr(2, 2, 64, 16, 4)
+    shapes = O.param_shapes(O.model_cfg(name="edsr"), 2, 2)
+    assert [k for k, _ in layout] == list(shapes.keys()) and [tuple(s_) for _, s_ in layout] == [tuple(v) for v in shapes.values()]
+    assert n == sum(int(np.prod(s_)) for _, s_ in layout)
+    assert lib.sres_rcan_num_segments(C.byref(d)) == 3
+    spans = []
+    for seg in range(3):
+        off, cnt = C.c_int64(), C.c_int64()
+        assert lib.sres_rcan_segment_params(C.byref(d), seg, C.byref(off), C.byref(cnt)) == 0
+        spans.append((off.value, cnt.value))
+    spans.sort()
+    assert spans[0][0] == 0 and all(a[0] + a[1] == b[0] for a, b in zip(spans, spans[1:])) and spans[-1][0] + spans[-1][1] == n
+    d.n_groups = 2
+    assert lib.sres_rcan_param_count(C.byref(d)) < 0          # EDSR is one group of ResBlocks
+    d.n_groups, d.res_scale = 1, 0.0
+    assert lib.sres_rcan_param_count(C.byref(d)) < 0          # res_scale must be positive
+    d.res_scale, d.arch = 1.0, 7
+    assert lib.sres_rcan_param_count(C.byref(d)) < 0          # unknown architecture
+
+
 def test_invalid_arguments_fail_loudly(lib):
     from sres_b200 import _lib as L
     from sres_b200.engine import RcanDesc
