@@ -35,7 +35,8 @@ struct ConvKParams {
   int npos;               // rows of the input PTL
   int n_tiles;            // 128-row tiles
   int nstage;             // smem ring depth
-  int stage_rows;         // rows per smem ring slot (multiple of kBoxRows)
+  int stage_rows;         // rows per smem ring slot (multiple of box_rows)
+  int box_rows;           // rows per TMA box of the A operand: the whole halo window when it fits one box (<= 256 rows)
   int n_out, c_real;
   unsigned flags;
   int map_mode, sub_i, sub_j, sf;
@@ -258,10 +259,10 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if constexpr (PAIR) {  // both CTAs' bytes complete on the leader CTA's barrier
           const uint32_t lbar = mapa_u32(smem_u32(&bar_full[slot]), 0);
           if (lead_cta) mbar_expect_tx(&bar_full[slot], 2 * stage_bytes);
-          for (int r = 0; r < p.stage_rows; r += kBoxRows) tma_load_2d_pair(dst + r * 128, &tmA, lbar, 0, row0 + r);
+          for (int r = 0; r < p.stage_rows; r += p.box_rows) tma_load_2d_pair(dst + r * 128, &tmA, lbar, 0, row0 + r);
         } else {
           mbar_expect_tx(&bar_full[slot], stage_bytes);
-          for (int r = 0; r < p.stage_rows; r += kBoxRows) tma_load_2d(dst + r * 128, &tmA, &bar_full[slot], 0, row0 + r);
+          for (int r = 0; r < p.stage_rows; r += p.box_rows) tma_load_2d(dst + r * 128, &tmA, &bar_full[slot], 0, row0 + r);
         }
       }
       __syncwarp();
@@ -741,7 +742,11 @@ static int launch_conv(const sres_conv_args* a, cudaStream_t stream) {
   const int tail_bytes = 1024;
   int slab_bytes = (p.use_o16 ? 16384 : 0) + (p.use_msk ? 16384 : 0) + ((p.use_r32 | p.use_o32) ? 32768 : 0);
   const int rows = 128 + 2 * (p.P + 1);
-  p.stage_rows = (rows + kBoxRows - 1) / kBoxRows * kBoxRows;
+  // one TMA box of the exact window (rounded to the 8-row swizzle atom) when it fits the 256-row box limit: fewer bytes
+  // into shared memory (232 instead of 256 rows at 48x48) and one TMA instruction per tile instead of four
+  const bool one_box = (rows + 7) / 8 * 8 <= 256 && !getenv("SRES_CONV_BOX64");
+  p.box_rows = one_box ? (rows + 7) / 8 * 8 : kBoxRows;
+  p.stage_rows = (rows + p.box_rows - 1) / p.box_rows * p.box_rows;
   int ns = (smem_max - 1024 - wbytes - tail_bytes - slab_bytes) / (p.stage_rows * 128);
   if (ns < 1 && p.tma_epi && !(a->epi_flags & SRES_EPI_DOT)) {  // wide image: give the slab space to the halo window
     p.tma_epi = p.use_o16 = p.use_msk = p.use_r32 = p.use_o32 = 0;
@@ -759,7 +764,7 @@ static int launch_conv(const sres_conv_args* a, cudaStream_t stream) {
   const size_t smem = (size_t)off + 1024;  // + alignment slack
 
   CUtensorMap tmA, tmW, tmO16, tmMsk, tmR32, tmO32;
-  int rc = make_tmap_rows64(&tmA, a->in_bf16, (uint64_t)p.npos, kBoxRows);
+  int rc = make_tmap_rows64(&tmA, a->in_bf16, (uint64_t)p.npos, p.box_rows);
   if (rc) return rc;
   rc = make_tmap_rows64(&tmW, a->wpack_bf16, (uint64_t)(9 * a->n_out), pair ? a->n_out / 2 : a->n_out);
   if (rc) return rc;
