@@ -16,6 +16,7 @@ struct CaGeom {
   int B, H, W, P, RP;   // RP = (H+1)*(W+1)
   int hid;              // F / reduction
   int blocks_per_image;
+  int tile_rows;        // output rows per M tile of the convolution that wrote the per-tile partial sums (126 or 128)
 };
 
 // ---- shared: s = sigmoid(W2 relu(W1 m + b1) + b2) for one image -----------------------------
@@ -135,11 +136,11 @@ ca_apply_fwd_kernel(CaGeom g, const uint16_t* __restrict__ t2, const float* __re
     sm_red[tid >> 6][tid & 63] = (tid < 64) ? pool_sum[b * 64 + tid] : 0.f;
   } else {
     const int c = tid & 63, part = tid >> 6;  // 4 partial sums per channel
-    const int t0 = (b * g.RP) / 128, t1 = ((b + 1) * g.RP - 1) / 128;
+    const int t0 = (b * g.RP) / g.tile_rows, t1 = ((b + 1) * g.RP - 1) / g.tile_rows;
     float a = 0.f;
 #pragma unroll 8
     for (int t = t0; t <= t1; ++t) {
-      const int seg = (t * 128 >= b * g.RP) ? 0 : 1;  // a tile that starts in the previous image holds this one as segment 1
+      const int seg = (t * g.tile_rows >= b * g.RP) ? 0 : 1;  // a tile that starts in the previous image holds this one as segment 1
       a += pool_part[(((size_t)t * 2 + seg) * 4 + part) * 64 + c];
     }
     sm_red[part][c] = a;
@@ -234,11 +235,11 @@ ca_bwd_apply_kernel(CaGeom g, const float* __restrict__ grad, const float* __res
   const int r0 = blockIdx.x * per_blk + (tid >> 3), r1 = min(g.RP, blockIdx.x * per_blk + per_blk);
   if (tile_part) {  // ds was reduced per M tile by the producing convolution (SRES_EPI_DOT)
     const int c = tid & 63, part = tid >> 6;
-    const int t0 = (b * g.RP) / 128, t1 = ((b + 1) * g.RP - 1) / 128;
+    const int t0 = (b * g.RP) / g.tile_rows, t1 = ((b + 1) * g.RP - 1) / g.tile_rows;
     float a = 0.f;
 #pragma unroll 8
     for (int t = t0; t <= t1; ++t) {
-      const int seg = (t * 128 >= b * g.RP) ? 0 : 1;
+      const int seg = (t * g.tile_rows >= b * g.RP) ? 0 : 1;
       a += tile_part[(((size_t)t * 2 + seg) * 4 + part) * 64 + c];
     }
     sm_dsr[part][c] = a;
@@ -394,6 +395,7 @@ static int ca_geom(CaGeom* g, int B, int H, int W, int hid) {
   if (bpi > max_bpi) bpi = max_bpi;
   if (bpi < 1) bpi = 1;
   g->blocks_per_image = bpi;
+  g->tile_rows = sres_conv_tile_rows(H, W);
   return SRES_OK;
 }
 

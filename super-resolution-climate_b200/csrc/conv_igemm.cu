@@ -718,6 +718,15 @@ static int launch_conv(const sres_conv_args* a, cudaStream_t stream) {
                                          a->out_nchw || (a->debug_flags & 2)))
     return set_error(SRES_ERR_INVALID_ARG, "conv: SRES_EPI_DOT needs mask_bf16 (the other factor), identity mapping, 64 outputs and no SRES_EPI_POOL");
 
+  // The RCAB loop's convolutions (identity mapping, TMA-staged epilogue, one fp32 addend at most) run on the
+  // three-taps-per-MMA kernel; debug_flags bit 6 (64) keeps them on this one for A/B runs and tests.
+  {
+    const bool ident_tma = a->map_mode == SRES_MAP_IDENT && a->n_out == 64 && !a->out_nchw && !a->resid2_f32 &&
+                           !(a->debug_flags & (2 | 4 | 8 | 32 | 64));
+    if (ident_tma && conv_n192_fits(a)) return launch_conv_n192(a, stream);
+    if ((a->epi_flags & (SRES_EPI_POOL | SRES_EPI_DOT)) && conv_n192_available(a->H, a->W) && !(a->debug_flags & (2 | 4 | 8 | 32 | 64)))
+      return set_error(SRES_ERR_UNSUPPORTED, "conv: with SRES_CONV_N192=2 per-tile partial sums need the identity-mapped TMA epilogue with one output and no second addend");
+  }
   ConvKParams p{};
   p.B = a->B; p.H = a->H; p.W = a->W; p.P = a->W + 1; p.R = a->H + 1;
   const long long npos = (long long)p.B * p.R * p.P;
@@ -829,9 +838,12 @@ static int launch_conv(const sres_conv_args* a, cudaStream_t stream) {
 
 }  // namespace sres
 
+extern "C" int sres_conv_tile_rows(int H, int W) { return sres::conv_n192_available(H, W) ? 126 : 128; }
+
 extern "C" int sres_conv_mtiles(int B, int H, int W) {
-  long long npos = (long long)B * (H + 1) * (W + 1);
-  return (int)((npos + 127) / 128);
+  const long long npos = (long long)B * (H + 1) * (W + 1);
+  const int tr = sres_conv_tile_rows(H, W);
+  return (int)((npos + tr - 1) / tr);
 }
 
 extern "C" int sres_conv_supported(int H, int W, int n_out) {

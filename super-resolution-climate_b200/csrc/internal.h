@@ -54,6 +54,11 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// N = 192 convolution kernel (conv_n192.cu): identity-mapped 64 -> 64 convolutions with TMA-staged epilogue operands
+bool conv_n192_available(int H, int W);
+bool conv_n192_fits(const sres_conv_args* a);
+int launch_conv_n192(const sres_conv_args* a, cudaStream_t stream);
+
 #define SRES_CHECK_LAUNCH(where)                                  \
   do {                                                            \
     cudaError_t e__ = cudaGetLastError();                         \

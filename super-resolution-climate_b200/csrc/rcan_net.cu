@@ -184,7 +184,7 @@ static int build_net(Net* n, const sres_rcan_desc* d, int training) {
   n->o_gf[0] = take(f32);
   n->o_gf[1] = take(f32);
   n->o_xf = take(f32);
-  n->o_pool_part = take((size_t)((r0 + 127) / 128) * 2 * 4 * 64 * 4);
+  n->o_pool_part = take((size_t)sres_conv_mtiles(d->B, d->H, d->W) * 2 * 4 * 64 * 4);
   n->o_pool_sum = take((size_t)d->B * 64 * 4);
   if (training) {
     n->o_ga = take(f32);

@@ -42,7 +42,9 @@ def test_header_cites_reference_lines():
 def test_geometry_helpers(lib):
     lib.sres_ptl_rows.restype = C.c_int64
     assert lib.sres_ptl_rows(64, 48, 48) == 64 * 49 * 49
-    assert lib.sres_conv_mtiles(64, 48, 48) == (64 * 49 * 49 + 127) // 128
+    tr = lib.sres_conv_tile_rows(48, 48)
+    assert tr in (126, 128)   # 126: three-taps-per-MMA kernel (tiles overlap by two rows)
+    assert lib.sres_conv_mtiles(64, 48, 48) == (64 * 49 * 49 + tr - 1) // tr
 
 
 def test_param_count_and_segments(lib):

@@ -42,32 +42,104 @@ def test_conv_forward_bias_relu_pool(env, B, H, W):
     nt = lib.sres_conv_mtiles(B, H, W)
     pool = torch.full((nt, 2, 4, 64), float("nan"), device=dev)
     fused = (H + 1) * (W + 1) >= 128
-    a = conv_args(in_bf16=xp, wpack_bf16=pack(lib, w.to(dev), 0), bias=b.to(dev), out_f32=out32, out_bf16=out16,
-                  B=B, H=H, W=W, n_out=64, epi_flags=L.EPI_RELU | (L.EPI_POOL if fused else 0))
+    wp, bd = pack(lib, w.to(dev), 0), b.to(dev)
+    # fp32 and bf16 outputs in separate calls (together they would not fit the N = 192 kernel's epilogue slabs)
+    a = conv_args(in_bf16=xp, wpack_bf16=wp, bias=bd, out_bf16=out16, B=B, H=H, W=W, n_out=64,
+                  epi_flags=L.EPI_RELU | (L.EPI_POOL if fused else 0))
     if fused:
         a.pool_part = pool.data_ptr()
     run_conv(lib, a)
+    run_conv(lib, conv_args(in_bf16=xp, wpack_bf16=wp, bias=bd, out_f32=out32, B=B, H=H, W=W, n_out=64, epi_flags=L.EPI_RELU))
     assert pads_are_zero(out32, B, H, W) and pads_are_zero(out16, B, H, W)
     assert rel_l2(from_ptl(out32, B, H, W).cpu(), ref) < 2e-3
     assert rel_l2(from_ptl(out16, B, H, W).cpu(), ref) < 6e-3          # + one bf16 rounding of the output
     if fused:
-        RP = (H + 1) * (W + 1)
-        sums = torch.zeros(B, 64)
-        pc = pool.cpu()
-        assert torch.isfinite(pc).all()
-        for t in range(nt):
-            b0 = (t * 128) // RP
-            for seg in range(2):
-                if b0 + seg < B:
-                    sums[b0 + seg] += pc[t, seg].sum(0)
-        assert rel_l2(sums, ref.sum((2, 3))) < 1e-4
+        assert torch.isfinite(pool).all()
+        assert rel_l2(image_sums(pool, B, H, W, lib.sres_conv_tile_rows(H, W)), ref.sum((2, 3))) < 1e-4
+
+
+def image_sums(part, B, H, W, tile_rows):
+    """[tile][segment][lane quarter][64] per-tile partial sums -> per-image channel sums [B][64]."""
+    RP = (H + 1) * (W + 1)
+    pc = part.detach().cpu().nan_to_num(0.0)
+    sums = torch.zeros(B, 64)
+    for t in range(pc.shape[0]):
+        b0 = (t * tile_rows) // RP
+        for seg in range(2):
+            if b0 + seg < B and t * tile_rows < B * RP:
+                sums[b0 + seg] += pc[t, seg].sum(0)
+    return sums
+
+
+@pytest.mark.parametrize("B,H,W", [(3, 20, 24), (5, 48, 48), (2, 96, 96)])
+def test_conv_n192_matches_tap_per_mma_kernel(env, B, H, W):
+    """The three-taps-per-MMA kernel (N = 192, shifted accumulator sum in the epilogue; debug flag 128 forces it for
+    every flavour it supports) against the tap-per-MMA kernel (debug flag 64) for every epilogue flavour: same operands, fp32 accumulation in a
+    different order, so fp32 outputs agree to 1e-5 relative and bf16 outputs to one rounding step."""
+    L, lib, dev = env
+    rows = lib.sres_ptl_rows(B, H, W)
+    nt = (rows + 125) // 126       # per-tile partial sums of the forced N = 192 kernel: 126-row tiles
+    xin = to_ptl(bf16_round(torch.randn(B, 64, H, W)).to(dev), torch.bfloat16)
+    msk = to_ptl(torch.randn(B, 64, H, W).to(dev), torch.bfloat16)
+    trunk = to_ptl(torch.randn(B, 64, H, W).to(dev), torch.float32)
+    wp = pack(lib, (torch.randn(64, 64, 3, 3) * 0.05).to(dev), 0)
+    bias = torch.randn(64, device=dev)
+    flavours = {
+        "conv1": dict(bias=bias, epi_flags=L.EPI_RELU, o16=True),
+        "conv2": dict(bias=bias, epi_flags=L.EPI_POOL, o16=True, part=True),
+        "dgrad2": dict(mask_bf16=msk, o16=True),
+        "dgrad1": dict(mask_bf16=msk, epi_flags=L.EPI_DOT, o32=True, rmw=True, part=True),
+        "group dgrad": dict(mask_bf16=msk, epi_flags=L.EPI_DOT, o32=True, part=True),
+        "group tail": dict(bias=bias, o16=True, o32=True, rmw=True),
+        "body tail": dict(bias=bias, o16=True, resid=True),
+        "plain fp32": dict(o32=True),
+    }
+    for name, f in flavours.items():
+        results = []
+        for dbg in (128, 128 | 16, 64):
+            out16 = torch.full((rows, 64), float("nan"), device=dev, dtype=torch.bfloat16)
+            out32 = trunk.clone() if f.get("rmw") else torch.full((rows, 64), float("nan"), device=dev)
+            part = torch.full((nt, 2, 4, 64), float("nan"), device=dev)
+            kw = dict(in_bf16=xin, wpack_bf16=wp, B=B, H=H, W=W, n_out=64, epi_flags=f.get("epi_flags", 0), debug_flags=dbg)
+            for k in ("bias", "mask_bf16"):
+                if k in f:
+                    kw[k] = f[k]
+            if f.get("o16"):
+                kw["out_bf16"] = out16
+            if f.get("o32"):
+                kw["out_f32"] = out32
+            if f.get("rmw"):
+                kw["resid_f32"] = out32
+            if f.get("resid"):
+                kw["resid_f32"] = trunk
+            if f.get("part"):
+                kw["pool_part"] = part
+            run_conv(lib, conv_args(**kw))
+            results.append((out16, out32, image_sums(part, B, H, W, 128 if dbg == 64 else 126)))
+            del kw
+        ref16, ref32, refp = results[2]
+        for out16, out32, psum in results[:2]:
+            if f.get("o16"):
+                assert torch.isfinite(out16.float()).all() and pads_are_zero(out16, B, H, W), name
+                # one bf16 rounding step at most, and only where the fp32 sums straddle a rounding boundary
+                d = (out16.float() - ref16.float()).abs()
+                assert bool((d <= 2.0 ** -7 * ref16.float().abs() + 1e-5).all()), name
+                assert float((d > 0).float().mean()) < 2e-2, name
+            if f.get("o32"):
+                assert torch.isfinite(out32).all() and pads_are_zero(out32, B, H, W), name
+                assert rel_l2(out32.cpu(), ref32.cpu()) < 1e-5, name
+            if f.get("part"):
+                assert rel_l2(psum, refp) < 1e-5, name
+        # the compile-time flavour and the runtime-flag instance of the same kernel are bit-equal
+        assert torch.equal(results[0][0].nan_to_num(0.0), results[1][0].nan_to_num(0.0)), name
+        assert torch.equal(results[0][1].nan_to_num(0.0), results[1][1].nan_to_num(0.0)), name
 
 
 @pytest.mark.parametrize("B,H,W", [(3, 20, 24), (5, 48, 48)])
 def test_conv_epilogue_flavours_agree(env, B, H, W):
-    """The compile-time epilogue flavours of the RCAB loop (default), their row-layout variant (debug 32), the generic
-    runtime-flag kernel (debug 16) and the opt-in CTA-pair kernel (debug 8) compute the same thing: outputs bit-equal,
-    per-tile partial sums equal up to summation order."""
+    """The tap-per-MMA kernel (debug flag 64; wide-image / PixelShuffle paths and the A/B baseline of the N = 192 kernel):
+    its compile-time epilogue flavours, their row-layout variant (+32), the generic runtime-flag kernel (+16) and the
+    opt-in CTA-pair kernel (+8) compute the same thing: outputs bit-equal, per-tile partial sums equal up to summation order."""
     L, lib, dev = env
     rows = lib.sres_ptl_rows(B, H, W)
     nt = lib.sres_conv_mtiles(B, H, W)
@@ -85,7 +157,7 @@ def test_conv_epilogue_flavours_agree(env, B, H, W):
     }
     for name, f in flavours.items():
         results = []
-        for dbg in (0, 32, 16, 8):
+        for dbg in (64, 64 | 32, 64 | 16, 64 | 8):
             out16 = torch.full((rows, 64), float("nan"), device=dev, dtype=torch.bfloat16)
             out32 = trunk.clone() if f.get("rmw") else torch.full((rows, 64), float("nan"), device=dev)
             part = torch.full((nt, 2, 4, 64), float("nan"), device=dev)
@@ -141,16 +213,8 @@ def test_conv_dgrad_mask_residuals(env, B, H, W):
         run_conv(lib, conv_args(in_bf16=dyp, wpack_bf16=wp, mask_bf16=to_ptl(t1.to(dev), torch.bfloat16), out_f32=out32,
                                 pool_part=part, B=B, H=H, W=W, n_out=64, epi_flags=L.EPI_DOT))
         assert rel_l2(from_ptl(out32, B, H, W).cpu(), dx) < 2e-3          # the mask operand must NOT gate the output
-        RP = (H + 1) * (W + 1)
-        sums = torch.zeros(B, 64)
-        pc = part.cpu()
-        assert torch.isfinite(pc).all()
-        for t in range(nt):
-            b0 = (t * 128) // RP
-            for seg in range(2):
-                if b0 + seg < B:
-                    sums[b0 + seg] += pc[t, seg].sum(0)
-        assert rel_l2(sums, (dx * t1).sum((2, 3))) < 2e-3
+        assert torch.isfinite(part).all()
+        assert rel_l2(image_sums(part, B, H, W, lib.sres_conv_tile_rows(H, W)), (dx * t1).sum((2, 3))) < 2e-3
 
 
 @pytest.mark.parametrize("f", [2, 3])

@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.join(ROOT, "super-resolution-climate_b200"))
 from sres_b200 import _lib as L
 lib = L.lib(); dev = torch.device("cuda:0")
 B, H, W = 64, 48, 48
-rows = lib.sres_ptl_rows(B, H, W); nt = lib.sres_conv_mtiles(B, H, W)
+rows = lib.sres_ptl_rows(B, H, W); nt = (rows + 125) // 126
 xin = (torch.randn(rows, 64, device=dev)).bfloat16()
 msk = (torch.randn(rows, 64, device=dev)).bfloat16()
 o16 = torch.zeros(rows, 64, device=dev, dtype=torch.bfloat16)
@@ -29,9 +29,10 @@ base = {
 }
 flav = {}
 for k, v in base.items():
-    flav[k + " specialised      "] = mk(**v)
-    if v.get("epi_flags", 0) & 6: flav[k + " specialised, rows"] = mk(debug_flags=32, **v)
-    flav[k + " generic kernel   "] = mk(debug_flags=16, **v)
+    flav[k + " N192 (forced)         "] = mk(debug_flags=128, **v)
+    flav[k + " N192 runtime flags    "] = mk(debug_flags=128 | 16, **v)
+    flav[k + " tap-per-MMA specialised"] = mk(debug_flags=64, **v)
+    flav[k + " N192 rt flags, NO shuffles (timing only)"] = mk(debug_flags=128 | 16 | 256, **v)
 st_ = L.cur_stream()
 for name, a in flav.items():
     for _ in range(5): L.check(lib.sres_conv3x3_igemm(C.byref(a), st_), name)
