@@ -75,6 +75,10 @@ def gen_model_case(name, over, B, S, C, loss_name, smooth, full_out):
         keep = ["head.0.weight", "head.0.bias", "tail.1.weight", "tail.1.bias", "body.0.body.0.body.0.bias",
                 "body.0.body.0.body.3.conv_du.0.weight", "body.0.body.0.body.3.conv_du.2.bias", f"body.{cfg['nlayers']}.bias"]
         w2 = "body.0.body.0.body.2.weight"
+        if cfg["nlayers"] > 4:   # full depth: also the far end of the body (last group, last RCAB, body-tail conv)
+            g, r = cfg["nlayers"] - 1, cfg["nblocks"] - 1
+            keep += [f"body.{g}.body.{r}.body.3.conv_du.0.weight", f"body.{g}.body.{r}.body.3.conv_du.2.bias",
+                     f"body.{g}.body.{r}.body.0.bias", f"body.{g}.body.{cfg['nblocks']}.bias", "tail.0.0.bias"]
     for k in keep:
         out["grad::" + k] = grads[k].numpy()
         out["post::" + k] = post[k].numpy()

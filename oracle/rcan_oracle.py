@@ -275,6 +275,15 @@ def loss_and_grads(hr: torch.Tensor, sd, cfg, loss_name: Optional[str] = None):
     return float(loss.item()), prd.detach(), {k: p.grad for k, p in params.items()}
 
 
+def forward_backward(lr_in: torch.Tensor, dout: torch.Tensor, sd, cfg):
+    """Model forward on an LR batch and the vector-Jacobian product with a given output gradient (autograd of
+    network.py:22-27, what mloss.backward() runs below the loss).  Returns (product, {key: grad})."""
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    prd = model_forward(lr_in, params, cfg)
+    prd.backward(dout)
+    return prd.detach(), {k: p.grad for k, p in params.items()}
+
+
 def train_step(hr, sd, cfg, adam: AdamState, loss_name: Optional[str] = None):
     """One optimizer step, in place on sd (dual_trainer.py:310-323)."""
     loss, prd, grads = loss_and_grads(hr, sd, cfg, loss_name)

@@ -41,6 +41,8 @@ MODEL_CASES = {
     "tiny_x8_4ch": (dict(nlayers=1, nblocks=1, downscale_factors=[2, 2, 2]), 1, 8, 4, "l2", False, True),
     "tiny_x3": (dict(nlayers=1, nblocks=1, downscale_factors=[3]), 2, 9, 2, "l2", False, True),
     "small_x4": (dict(nlayers=4, nblocks=4), 4, 48, 2, "l2", True, False),
+    # BASELINE config 2 depth (10 groups x 20 RCABs, reduction 16) on a batch the reference's CPU path finishes in seconds
+    "full_x4_r16": (dict(nlayers=10, nblocks=20, cbottleneck=16), 2, 48, 2, "l2", True, False),
     # EDSR through the same factory (sres/model/edsr/network.py)
     "edsr_tiny_x4": (dict(name="edsr", nlayers=3), 2, 12, 2, "l2", False, True),
     "edsr_x2_rs01_charb": (dict(name="edsr", nlayers=2, res_scale=0.1, downscale_factors=[2], loss_fn="charbonnier"), 3, 10, 1,

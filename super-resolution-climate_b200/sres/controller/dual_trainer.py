@@ -255,7 +255,7 @@ class ModelTrainer(object):
         timeslice = self.load_timeslice(ctime)
         vnames, cvar = self.target_variables, kwargs.get("var", None)
         output_vars = [cvar] if cvar is not None else vnames
-        batch_model_losses, batch_interp_losses, batches = [], [], []
+        model_losses, interp_losses, batches, stats = [], [], [], []
         tile_iter = TileIterator.get_iterator(ntiles=timeslice.sizes["tiles"])
         ctiles = list(iter(tile_iter))
         # data parallel: rank r runs the forward on a contiguous range of the tile batches; the products are gathered
@@ -268,11 +268,16 @@ class ModelTrainer(object):
                     break
                 binput, boutput, btarget = self.apply_network(batch_data)
                 binterp = upsample(binput)
-                batch_model_losses.append(self.loss(boutput, btarget)[0])
-                batch_interp_losses.append(self.loss(binterp, btarget)[0])
-                a = batch_data.attrs
-                batches.append(dict(input=denorm(binput, a), target=denorm(btarget, a), interpolated=denorm(binterp, a),
-                                    model=denorm(boutput, a)))
+                # the per-batch losses stay on the device: one host sync per image, not two per batch
+                model_losses.append(self.single_product_loss(boutput, btarget))
+                interp_losses.append(self.single_product_loss(binterp, btarget))
+                # products stay normalised; x*std+mean (dual_trainer.py:67-77) is fused into the stitch kernel
+                batches.append(dict(input=binput, target=btarget, interpolated=binterp, model=boutput))
+                stats.append(batch_data.attrs)
+        nb = len(model_losses)
+        lsum = torch.stack([torch.stack(model_losses).double().sum(), torch.stack(interp_losses).double().sum(),
+                            torch.tensor(float(nb), dtype=torch.float64, device=self.device)]) if nb else \
+            torch.zeros(3, dtype=torch.float64, device=self.device)
         if self.world > 1:
             ntiles = int(timeslice.sizes["tiles"])
             counts = []   # tile rows per rank (equal batch sizes except the last batch)
@@ -284,40 +289,54 @@ class ModelTrainer(object):
             merged = {}
             for k in ("input", "target", "interpolated", "model"):
                 side = hr // scale if k == "input" else hr // int(cfg().task.get("data_downsample", 1.0))
-                local = torch.cat([torch.as_tensor(bd[k], device=self.device).float() for bd in batches], dim=0) if batches else None
+                local = torch.cat([denorm(bd[k], a).float() for bd, a in zip(batches, stats)], dim=0) if batches else None
                 merged[k] = gather_rows(local, counts, (nch, side, side), self.device)
-            batches = [merged]
-            stat = torch.tensor([float(np.sum(batch_model_losses)), float(np.sum(batch_interp_losses)), float(len(batch_model_losses))],
-                                dtype=torch.float64, device=self.device)
-            dist.all_reduce(stat)
-            batch_model_losses, batch_interp_losses = [float(stat[0] / stat[2])], [float(stat[1] / stat[2])]
+            batches, stats = [merged], None
+            dist.all_reduce(lsum)
+        lsum = lsum.cpu()
+        mean_model = float(lsum[0] / lsum[2]) if float(lsum[2]) > 0 else float("nan")
+        mean_interp = float(lsum[1] / lsum[2]) if float(lsum[2]) > 0 else float("nan")
         images, losses = {}, {}
         for ivar, vname in enumerate(output_vars):
-            images[vname] = self.assemble_images(batches, ivar, timeslice.coords["tiles"], timeslice.attrs["grid_shape"])
-            losses[vname] = dict(model=float(np.array(batch_model_losses).mean()),
-                                 interpolated=float(np.array(batch_interp_losses).mean()))
+            images[vname] = self.assemble_images(batches, ivar, timeslice.coords["tiles"], timeslice.attrs["grid_shape"], stats)
+            losses[vname] = dict(model=mean_model, interpolated=mean_interp)
         return images, losses
 
-    def assemble_images(self, batches: List[Dict[str, Tensor]], ivar: int, tile_ids, grid_shape: Dict[str, int]) -> Dict[str, np.ndarray]:
-        """Place tile `tid` at grid cell (tid // gx, tid % gx), NaN elsewhere (dual_trainer.py:449-480), on
-        the GPU.  dtype rule of the reference's np.block: float64 iff at least one cell stayed empty."""
+    def assemble_images(self, batches: List[Dict[str, Tensor]], ivar: int, tile_ids, grid_shape: Dict[str, int],
+                        norm_stats: Optional[List[Dict[str, Any]]] = None) -> Dict[str, np.ndarray]:
+        """Place tile `tid` at grid cell (tid // gx, tid % gx), NaN elsewhere (dual_trainer.py:449-480), on the GPU.
+        norm_stats (one dict(mean, std) of shape (B,C,1,1) per batch): the tiles are normalised and the kernel
+        de-normalises them, x*std+mean, while it places them (`denorm`, dual_trainer.py:67-77, same two fp32 roundings).
+        dtype rule of the reference's np.block: float64 iff at least one cell stayed empty (its placeholder is a
+        float64 NaN tile); the widening runs on the device and every image reaches the host through ONE copy into
+        pinned memory (torch's caching host allocator recycles the buffers of images the caller has dropped)."""
         lib = L.lib()
         gy, gx = int(grid_shape["y"]), int(grid_shape["x"])
         tile_ids = np.asarray(tile_ids)
-        out: Dict[str, np.ndarray] = {}
+        mean = std = None
+        if norm_stats is not None:
+            if any("max" in a for a in norm_stats):
+                raise NotImplementedError("sres (B200 build): min/max de-normalisation has no CUDA kernel (lnorm only)")
+            mean = torch.cat([torch.as_tensor(a["mean"], device=self.device).float().reshape(-1) for a in norm_stats]).contiguous()
+            std = torch.cat([torch.as_tensor(a["std"], device=self.device).float().reshape(-1) for a in norm_stats]).contiguous()
+        pending: Dict[str, Tensor] = {}
         for image_type in batches[0].keys():
-            tiles = torch.cat([torch.as_tensor(b[image_type], device=self.device).float() for b in batches], dim=0).contiguous()
+            tiles = torch.cat([torch.as_tensor(b[image_type], device=self.device).detach().float() for b in batches], dim=0).contiguous()
             n, Cc, t, _ = tiles.shape
             cell = np.full(gy * gx, -1, dtype=np.int32)
-            for i in range(n):           # later tiles overwrite earlier ones, like the reference's loop
-                cell[int(tile_ids[i])] = i
+            cell[tile_ids[:n].astype(np.int64)] = np.arange(n, dtype=np.int32)   # (ids are unique: later == earlier)
             cell_d = torch.from_numpy(cell).to(self.device)
             img = torch.empty(gy * t, gx * t, dtype=torch.float32, device=self.device)
-            L.check(lib.sres_tiles_stitch(L.ptr(tiles), Cc, ivar, t, gy, gx, L.ptr(cell_d), None, None, L.ptr(img),
+            if mean is not None and mean.numel() != n * Cc:
+                raise ValueError(f"assemble_images: {mean.numel()} normalisation entries for {n} tiles x {Cc} channels")
+            L.check(lib.sres_tiles_stitch(L.ptr(tiles), Cc, ivar, t, gy, gx, L.ptr(cell_d), L.ptr(mean), L.ptr(std), L.ptr(img),
                                           L.cur_stream()), "sres_tiles_stitch")
-            arr = img.cpu().numpy()   # (widening on the device first was measured slower: the pageable 8-byte copy dominates)
-            out[image_type] = arr.astype(np.float64) if (cell < 0).any() else arr
-        return out
+            dev_img = img.double() if (cell < 0).any() else img
+            host = torch.empty(dev_img.shape, dtype=dev_img.dtype, pin_memory=True)
+            host.copy_(dev_img, non_blocking=True)
+            pending[image_type] = host
+        torch.cuda.current_stream().synchronize()
+        return {k: v.numpy() for k, v in pending.items()}
 
     def evaluate(self, tset: TSet, **kwargs):
         """Batched forward over the tiles of a validation/test timeslice (dual_trainer.py:482-543).

@@ -67,11 +67,43 @@ def test_train_step_matches_oracle_and_golden(name, dev, golden_dir):
     gn = np.array([p.grad.double().norm().item() for _, p in model.named_parameters()])
     big = gold["grad_norms"] > 0.05 * gold["grad_norms"].max()
     np.testing.assert_allclose(gn[big], gold["grad_norms"][big], rtol=3e-2)
-    for key in ("head.0.weight", "tail.1.weight", "tail.1.bias"):
-        g = dict(model.named_parameters())[key].grad.cpu().numpy()
-        assert np.linalg.norm(g - gold["grad::" + key]) / np.linalg.norm(gold["grad::" + key]) < 2 * TOL
-    # exact identity: d loss / d tail bias = sum of the output gradient
+    # every tensor the fixture holds in full -- conv and channel-attention weights and biases at both ends of the body, head and
+    # tail: per-tensor rel-L2 against the REFERENCE's gradient, <= 2e-2 each (measured 4e-4 ... 1.2e-2).  One documented
+    # exception (deviation 3): the bias of an RCAB's FIRST conv in the white-noise cases on 8..12-pixel
+    # tiles.  Its gradient is sum_q relu'(t1[q]) * g[q] over only ~150-300 positions with random signs; bf16 operand rounding
+    # flips the ReLU mask of about one position in 300 and ONE flipped term moves such a cancellation-heavy sum by a few %
+    # (measured 3.9e-2 ... 5.3e-2).  With smooth fields / 48-pixel tiles (2304+ positions) the same tensors sit at 3e-3 ... 8e-3.
+    params = dict(model.named_parameters())
+    worst = {}
+    for gk in [k for k in gold.files if k.startswith("grad::") and "[" not in k]:
+        key = gk[len("grad::"):]
+        g = params[key].grad.cpu().numpy()
+        worst[key] = float(np.linalg.norm(g - gold[gk]) / (np.linalg.norm(gold[gk]) + 1e-30))
+    print(name, "per-tensor gradient rel-L2 vs reference:", {k: f"{v:.2e}" for k, v in worst.items()})
+    for key, err in worst.items():
+        conv1_bias = key.endswith(".body.0.bias") and not smooth
+        assert err < (8 * TOL if conv1_bias else 2 * TOL), (key, err, worst)
+    # one fused Adam step from the GPU's OWN gradients against the reference's post-step parameters.  The first Adam step
+    # moves every element by lr * g / (|g| + eps), i.e. by +-lr wherever |g| >> eps: the update direction only differs where
+    # a gradient element is within rounding distance of zero.
+    pre = {k: p.detach().clone() for k, p in model.named_parameters()}
+    opt.step()
+    torch.cuda.synchronize()
+    frac_off = {}
+    for pk in [k for k in gold.files if k.startswith("post::")]:
+        key = pk[len("post::"):]
+        d_gpu = (params[key].detach() - pre[key]).cpu().numpy()
+        d_ref = gold[pk] - sd[key].numpy()
+        assert np.abs(d_gpu).max() <= 1.0001e-4 and np.abs(d_ref).max() <= 1.0001e-4
+        n_off = int((np.abs(d_gpu - d_ref) > 2e-5).sum())
+        frac_off[key] = n_off / d_ref.size
+        assert n_off <= max(2, d_ref.size // 100), (key, n_off, d_ref.size)     # measured: 0-2 elements, <= 0.9 % of big tensors
+    print(name, "fraction of elements whose first Adam update differs from the reference's:", {k: f"{v:.1e}" for k, v in frac_off.items()})
+    gpost = np.array([p.detach().double().norm().item() for _, p in model.named_parameters()])
+    np.testing.assert_allclose(gpost, gold["post_norms"], rtol=5e-4)   # every parameter tensor after the GPU-computed step
     # one fused Adam step from the oracle's gradients must reproduce the oracle's Adam
+    model.load_state_dict(O.make_state_dict(cfg, C, C))
+    opt = snn.FusedAdam(model, lr=1e-4)
     with torch.no_grad():
         for k, p in model.named_parameters():
             p.grad.copy_(grads_o[k])
@@ -164,6 +196,49 @@ def test_full_size_properties(dev):
     names = [k for k, _ in eng.layout]
     off = sum(int(np.prod(s_)) for _, s_ in eng.layout[:names.index("tail.1.bias")])
     assert rel_l2(g[off:off + 2], dout.sum((0, 2, 3))) < 1e-5
+
+
+def test_full_size_batch_tiles_match_oracle(dev):
+    """BASELINE config 2 at full size (RCAN-full x4, reduction 16, 64 tiles of 2x48x48) against the ORACLE: tiles are
+    independent units, so the oracle runs on four of the 64 tiles and must reproduce those four outputs of the batch-64 GPU
+    pass; with an output gradient that is zero outside those tiles the batch-64 parameter gradients equal the oracle's
+    gradients of the four-tile problem (head, tail, channel-attention and conv tensors compared one by one, the
+    full gradient globally)."""
+    cfg = O.model_cfg(cbottleneck=16)
+    sd = O.make_state_dict(cfg, 2, 2)
+    model = _build(cfg, 2, dev)
+    model.load_state_dict(sd)
+    eng = model.engine
+    from sres_b200 import nn as snn
+    hr = synth_hr(64, 2, 192, smooth=True)
+    x = snn.bicubic_resize(hr.to(dev), 0.25).contiguous()
+    pick = [0, 21, 42, 63]
+    out = eng.forward(x, training=True).clone()
+    # oracle on the four tiles (fp32 CPU restatement of the reference network + autograd); the output gradient is the
+    # RMSE gradient of the four-tile problem (stats.py:5-8), handed to both sides
+    xs = x[pick].cpu()
+    prd4 = O.model_forward(xs, sd, cfg)
+    diff = prd4 - hr[pick]
+    dsel = (diff / (diff.numel() * torch.sqrt((diff * diff).mean()))).contiguous()
+    prd_o, grads_o = O.forward_backward(xs, dsel, sd, cfg)
+    dout = torch.zeros(64, 2, 192, 192)
+    dout[pick] = dsel
+    eng.backward(x, dout.to(dev), accumulate=False)
+    grad = eng.flat_grad.clone().cpu()
+    assert rel_l2(out[pick].cpu(), prd_o) < TOL
+    off, num, den, per = 0, 0.0, 0.0, {}
+    for k, shp in eng.layout:
+        n = int(np.prod(shp))
+        gg, go = grad[off:off + n].double(), grads_o[k].reshape(-1).double()
+        num += (gg - go).pow(2).sum().item(); den += go.pow(2).sum().item()
+        if k in ("head.0.weight", "head.0.bias", "tail.1.weight", "tail.1.bias", "tail.0.0.weight", "body.10.weight",
+                 "body.0.body.0.body.3.conv_du.0.weight", "body.9.body.19.body.3.conv_du.2.bias", "body.9.body.20.bias",
+                 "body.4.body.7.body.2.weight"):
+            per[k] = float((gg - go).norm() / (go.norm() + 1e-30))
+        off += n
+    print(f"batch 64, four tiles vs oracle: output {rel_l2(out[pick].cpu(), prd_o):.3e}, gradient {(num / den) ** 0.5:.3e},",
+          {k: f"{v:.2e}" for k, v in per.items()})
+    assert (num / den) ** 0.5 < TOL and max(per.values()) < 2 * TOL, per
 
 
 def test_gradient_accumulation_and_stock_adam(dev):
@@ -296,6 +371,20 @@ def test_tiles_extract_norm_flip_stitch_bit_exact(name, dev, golden_dir):
                 assert imgs_g[k].dtype == imgs_o[k].dtype and sha(imgs_g[k]) == sha(imgs_o[k])
                 assert int(np.isnan(imgs_g[k]).sum()) == int(gold[f"image_{ivar}_{k}_nan"])
                 assert list(imgs_g[k].shape) == list(gold[f"image_{ivar}_{k}_shape"])
+        # de-normalise + stitch (dual_trainer.py:67-77 + :449-480) fused in the stitch kernel: fed with the oracle's
+        # normalised batches and statistics (pinned bit for bit to the reference, tests/test_oracle_golden.py) the images
+        # must hash to the REFERENCE's images, dtype rule included
+        nbatches, nstats = [], []
+        for b in T.tile_batches(tiles_o.shape[0], 7):
+            bd, st = T.lnorm(T.select_batch(tiles_o, b["start"], b["end"]))
+            nbatches.append({"input": torch.from_numpy(np.ascontiguousarray(bd[:, :, ::scale, ::scale])).to(dev),
+                             "target": torch.from_numpy(bd).to(dev)})
+            nstats.append({k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in st.items()})
+        for ivar in range(C):
+            imgs = tr.assemble_images(nbatches, ivar, ts.coords["tiles"], ts.attrs["grid_shape"], nstats)
+            for k, img in imgs.items():
+                assert str(img.dtype) == str(gold[f"image_{ivar}_{k}_dtype"])
+                assert sha(img) == str(gold[f"image_{ivar}_{k}_sha"]), (name, ivar, k)
     finally:
         ConfigContext.deactivate()
 
