@@ -12,8 +12,9 @@
  * Each entry point below names the reference lines it replaces.  Signatures are plain C: raw
  * device pointers, explicit sizes, a cudaStream_t passed as void*.  Every function returns an
  * int status (SRES_OK == 0), never throws, never allocates device memory (the caller owns all
- * buffers, including workspaces) and keeps no mutable global state, so calls on different
- * streams are independent.  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ * buffers, including workspaces), so calls on different streams are independent.  Process-wide state is limited to
+ * read-once environment switches, the L2 set-aside flag of sres_l2_set_aside and the optional
+ * SRES_PROFILE event list; none of it is touched by the data path after the first call.  INTEGRATION.md shows the ctypes binding a maintainer would add.
  *
  * Activation layout ("padded tile layout", PTL).  A batch of B feature maps of H x W pixels with
  * 64 channels is stored as   rows = B*(H+1)*(W+1) positions,  64 channels per position,
@@ -216,15 +217,19 @@ SRES_API int sres_bicubic_resize(const float* in, float* out, int planes, int Hi
 /* Losses: kind 0 = l2 / RMSE (sres/controller/stats.py:5-8), 1 = charbonnier                  */
 /* (sres/controller/dual_trainer.py:196-198), 2 = l1 (BASELINE north_star variant).            */
 /* The target plane (tH,tW) may exceed the product's (H,W): conform_to_product,                */
-/* dual_trainer.py:200-203.  stat: device double[2]; stat[0] = sum_i f(d_i) of THIS rank --    */
-/* a data-parallel caller all-reduces stat[0] before sres_loss_value.           */
+/* dual_trainer.py:200-203.  stat: device double[2]; stat[0] = sum_i f(d_i) and stat[1] = number */
+/* of elements of THIS rank -- a data-parallel caller all-reduces both (sum) and passes          */
+/* n_total_dev = stat + 1, so ranks with batches of different sizes agree on the global-batch    */
+/* loss.  n_total_dev == NULL: the element count is the host value n_total.       */
 /* ------------------------------------------------------------------------------------------ */
 SRES_API size_t sres_loss_workspace_bytes(void);
 SRES_API int sres_loss_sum(const float* prd, const float* tgt, int planes, int H, int W, int tH, int tW, int kind,
                            double* stat, void* workspace, size_t workspace_bytes, void* stream);
-SRES_API int sres_loss_value(const double* stat, double n_total, int kind, float* loss, void* stream);
+SRES_API int sres_loss_value(const double* stat, double n_total, const double* n_total_dev, int kind, float* loss,
+                             void* stream);
 SRES_API int sres_loss_grad(const float* prd, const float* tgt, int planes, int H, int W, int tH, int tW, int kind,
-                            const float* loss, double n_total, float gscale, const float* gscale_dev, float* grad,
+                            const float* loss, double n_total, const double* n_total_dev, float gscale,
+                            const float* gscale_dev, float* grad,
                             void* stream); /* upstream factor = gscale * (gscale_dev ? *gscale_dev : 1) */
 
 /* ------------------------------------------------------------------------------------------ */

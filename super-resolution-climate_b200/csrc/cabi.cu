@@ -121,7 +121,7 @@ int make_tmap_rows64_half(CUtensorMap* out, const void* base, uint64_t nrows, ui
 
 }  // namespace sres
 
-extern "C" int sres_abi_version(void) { return 2; }  // 2: sres_rcan_desc.arch/res_scale, sres_wgrad_job.scale
+extern "C" int sres_abi_version(void) { return 3; }  // 3: device-side element count of the losses, sres_conv_tile_rows
 extern "C" const char* sres_last_error(void) { return sres::t_err; }
 extern "C" int sres_device_sm_count(void) { return sres::device_sm_count(); }
 extern "C" int64_t sres_ptl_rows(int B, int H, int W) { return (int64_t)B * (H + 1) * (W + 1); }

@@ -104,19 +104,24 @@ loss_partial_kernel(const float* __restrict__ prd, const float* __restrict__ tgt
   if (threadIdx.x == 0) part[blockIdx.x] = sm[0];
 }
 
-// stat (double[2]): [0] = sum over THIS rank, [1] unused here.
-__global__ void loss_final_kernel(const double* __restrict__ part, int nparts, double* __restrict__ stat) {
+// stat (double[2]): [0] = sum over THIS rank, [1] = number of elements of THIS rank -- a data-parallel caller all-reduces
+// both, so that ranks holding batches of different sizes (the short last batch of a timeslice) still agree on the
+// global-batch loss.
+__global__ void loss_final_kernel(const double* __restrict__ part, int nparts, double n_local, double* __restrict__ stat) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double s = 0.0;
     for (int i = 0; i < nparts; ++i) s += part[i];
     stat[0] = s;
+    stat[1] = n_local;
   }
 }
 
 // loss value from the (possibly all-reduced) sum:  l2: sqrt(sum/N),  others: sum/N.
-__global__ void loss_value_kernel(const double* __restrict__ stat, double n_total, int kind, float* __restrict__ loss) {
+__global__ void loss_value_kernel(const double* __restrict__ stat, double n_total, const double* __restrict__ n_total_dev,
+                                  int kind, float* __restrict__ loss) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    const double m = stat[0] / n_total;
+    if (n_total_dev) n_total = n_total_dev[0];
+    const double m = n_total > 0.0 ? stat[0] / n_total : 0.0;   // (no elements anywhere: define the loss as 0)
     loss[0] = (float)(kind == 0 ? sqrt(m) : m);
   }
 }
@@ -125,12 +130,13 @@ __global__ void loss_value_kernel(const double* __restrict__ stat, double n_tota
 //   l2:  d / (N * L);  charbonnier: d / sqrt(d^2+eps) / N;  l1: sign(d) / N      (N = n_total)
 __global__ void __launch_bounds__(256)
 loss_grad_kernel(const float* __restrict__ prd, const float* __restrict__ tgt, LossGeom g, int kind, float eps,
-                 const float* __restrict__ loss, double n_total, float gscale, const float* __restrict__ gscale_dev,
-                 float* __restrict__ grad) {
+                 const float* __restrict__ loss, double n_total, const double* __restrict__ n_total_dev, float gscale,
+                 const float* __restrict__ gscale_dev, float* __restrict__ grad) {
   const float L = loss[0];
   if (gscale_dev) gscale *= gscale_dev[0];
-  const float inv_n = (float)(1.0 / n_total);
-  const float k_l2 = gscale * inv_n / L;
+  if (n_total_dev) n_total = n_total_dev[0];
+  const float inv_n = n_total > 0.0 ? (float)(1.0 / n_total) : 0.f;
+  const float k_l2 = (gscale != 0.f && L > 0.f) ? gscale * inv_n / L : 0.f;   // weight-0 participant / zero loss: no gradient
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += (long long)gridDim.x * blockDim.x) {
     const float d = prd[i] - tgt[tgt_index(g, i)];
     float r;
@@ -202,27 +208,28 @@ extern "C" int sres_loss_sum(const float* prd, const float* tgt, int planes, int
   if (workspace_bytes < (size_t)grid * sizeof(double)) return set_error(SRES_ERR_INVALID_ARG, "loss: workspace too small");
   loss_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(prd, tgt, g, kind, 1e-6f, (double*)workspace);
   SRES_CHECK_LAUNCH("loss: partial launch");
-  loss_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const double*)workspace, grid, stat);
+  loss_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const double*)workspace, grid, (double)g.n, stat);
   SRES_CHECK_LAUNCH("loss: final launch");
   return SRES_OK;
 }
 
-extern "C" int sres_loss_value(const double* stat, double n_total, int kind, float* loss, void* stream) {
-  if (!stat || !loss || n_total <= 0) return set_error(SRES_ERR_INVALID_ARG, "loss_value: bad argument");
-  loss_value_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(stat, n_total, kind, loss);
+extern "C" int sres_loss_value(const double* stat, double n_total, const double* n_total_dev, int kind, float* loss,
+                               void* stream) {
+  if (!stat || !loss || (!n_total_dev && n_total <= 0)) return set_error(SRES_ERR_INVALID_ARG, "loss_value: bad argument");
+  loss_value_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(stat, n_total, n_total_dev, kind, loss);
   SRES_CHECK_LAUNCH("loss_value: launch");
   return SRES_OK;
 }
 
 extern "C" int sres_loss_grad(const float* prd, const float* tgt, int planes, int H, int W, int tH, int tW, int kind,
-                              const float* loss, double n_total, float gscale, const float* gscale_dev, float* grad,
-                              void* stream) {
+                              const float* loss, double n_total, const double* n_total_dev, float gscale,
+                              const float* gscale_dev, float* grad, void* stream) {
   LossGeom g;
   int rc = loss_geom(&g, planes, H, W, tH, tW);
   if (rc) return rc;
-  if (!prd || !tgt || !loss || !grad || n_total <= 0) return set_error(SRES_ERR_INVALID_ARG, "loss_grad: bad argument");
-  loss_grad_kernel<<<ew_grid(g.n, 4), 256, 0, (cudaStream_t)stream>>>(prd, tgt, g, kind, 1e-6f, loss, n_total, gscale,
-                                                                      gscale_dev, grad);
+  if (!prd || !tgt || !loss || !grad || (!n_total_dev && n_total <= 0)) return set_error(SRES_ERR_INVALID_ARG, "loss_grad: bad argument");
+  loss_grad_kernel<<<ew_grid(g.n, 4), 256, 0, (cudaStream_t)stream>>>(prd, tgt, g, kind, 1e-6f, loss, n_total, n_total_dev,
+                                                                      gscale, gscale_dev, grad);
   SRES_CHECK_LAUNCH("loss_grad: launch");
   return SRES_OK;
 }

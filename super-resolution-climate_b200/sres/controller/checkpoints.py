@@ -1,9 +1,17 @@
-"""Checkpoint files, mirror of sres/controller/checkpoints.py:11-67 (same path scheme and dict keys, so
-files interchange with the reference: model_state_dict holds fp32 tensors under the reference's names)."""
+"""Checkpoint files of the trainer.
+
+Same file scheme and dictionary layout as the reference's CheckpointManager (sres/controller/checkpoints.py:11-67):
+`{platform.results}/checkpoints/{task.training_version}.{train|valid}.pt` holding
+{epoch, itime, model_state_dict, optimizer_state_dict, loss}.  model_state_dict carries fp32 tensors under the
+reference's parameter names and optimizer_state_dict has torch.optim.Adam's layout (sres_b200.nn.FusedAdam reads
+and writes it), so checkpoints move between this build and the reference in both directions.
+
+Unlike the reference, a checkpoint that exists but cannot be applied is an error, not a silent restart from
+scratch: the optimizer state is validated BEFORE the model weights are touched.
+"""
 import os
 import shutil
 import time
-import traceback
 from typing import Any, Dict, Optional
 
 import torch
@@ -12,55 +20,52 @@ from sres.base.util.config import cfg
 from sres.controller.config import TSet
 
 
-class CheckpointManager(object):
+class CheckpointError(RuntimeError):
+    pass
+
+
+class CheckpointManager:
 
     def __init__(self, model, optimizer):
-        self.model = model
-        self.optimizer = optimizer
+        self.model, self.optimizer = model, optimizer
 
-    def save_checkpoint(self, epoch: int, itime: int, tset: TSet, loss: float, interp_loss: float) -> str:
-        t0 = time.time()
-        checkpoint = dict(epoch=epoch, itime=itime, model_state_dict=self.model.state_dict(),
-                          optimizer_state_dict=self.optimizer.state_dict(), loss=loss)
-        cpath = self.checkpoint_path(tset)
-        if os.path.isfile(cpath):
-            shutil.copyfile(cpath, self.checkpoint_path(tset, backup=True))
-        torch.save(checkpoint, cpath)
-        print(f" *** SAVE {tset.name} checkpoint, loss={loss:.5f} ({interp_loss:.5f}), to {cpath}, dt={time.time()-t0:.4f} sec")
-        return cpath
+    @staticmethod
+    def checkpoint_path(tset: TSet, backup: bool = False) -> str:
+        which = TSet.Validation if tset == TSet.Test else tset     # test shares the validation file
+        folder = os.path.join(str(cfg().platform.results), "checkpoints")
+        os.makedirs(folder, mode=0o777, exist_ok=True)
+        stem = f"{cfg().task.training_version}.{which.value}" + (".backup" if backup else "")
+        return os.path.join(folder, stem + ".pt")
 
-    def _load_state(self, tset: TSet) -> Dict[str, Any]:
-        return torch.load(self.checkpoint_path(tset), map_location="cpu", weights_only=False)
+    def save_checkpoint(self, epoch: int, itime: int, tset: TSet, loss: float, interp_loss: float = float("nan")) -> str:
+        started = time.time()
+        path = self.checkpoint_path(tset)
+        if os.path.isfile(path):
+            shutil.copyfile(path, self.checkpoint_path(tset, backup=True))
+        payload = {"epoch": epoch, "itime": itime, "model_state_dict": self.model.state_dict(),
+                   "optimizer_state_dict": self.optimizer.state_dict(), "loss": loss}
+        torch.save(payload, path)
+        print(f" *** SAVE {tset.name} checkpoint, loss={loss:.5f} ({interp_loss:.5f}), to {path}, dt={time.time() - started:.4f} sec")
+        return path
 
-    def load_checkpoint(self, tset: TSet = TSet.Train, **kwargs) -> Optional[Dict[str, Any]]:
-        update_model = kwargs.get("update_model", False)
-        cppath = self.checkpoint_path(tset)
-        train_state = {}
-        if os.path.exists(cppath):
+    def load_checkpoint(self, tset: TSet = TSet.Train, update_model: bool = False, **_ignored) -> Optional[Dict[str, Any]]:
+        """The training state {epoch, itime, loss} of the checkpoint, {} when there is no file yet.  With update_model the
+        optimizer state and then the weights are restored; a file that does not fit raises CheckpointError."""
+        path = self.checkpoint_path(tset)
+        if not os.path.exists(path):
+            print(f"No checkpoint file found at '{path}': starting from scratch.")
+            return {}
+        state = torch.load(path, map_location="cpu", weights_only=False)
+        if update_model:
             try:
-                train_state = self._load_state(tset)
-                if update_model:
-                    self.model.load_state_dict(train_state.pop("model_state_dict"))
-                    self.optimizer.load_state_dict(train_state.pop("optimizer_state_dict"))
-            except Exception as e:
-                print(f"Unable to load model from {cppath}: {e}")
-                traceback.print_exc()
-                return None
-        else:
-            print(f"No checkpoint file found at '{cppath}': starting from scratch.")
-        return train_state
+                self.optimizer.load_state_dict(state.pop("optimizer_state_dict"))   # validates before anything changes
+                self.model.load_state_dict(state.pop("model_state_dict"))
+            except Exception as err:
+                raise CheckpointError(f"checkpoint {path} does not fit this model / optimizer: {err}") from err
+        return state
 
-    def clear_checkpoints(self):
-        for tset in [TSet.Train, TSet.Validation]:
-            cppath = self.checkpoint_path(tset)
-            if os.path.exists(cppath):
-                os.remove(cppath)
-
-    @classmethod
-    def checkpoint_path(cls, tset: TSet, backup=False) -> str:
-        vtset: TSet = TSet.Validation if (tset == TSet.Test) else tset
-        cpath = f"{cfg().platform.results}/checkpoints/{cfg().task.training_version}.{vtset.value}"
-        if backup:
-            cpath = f"{cpath}.backup"
-        os.makedirs(os.path.dirname(cpath), 0o777, exist_ok=True)
-        return cpath + ".pt"
+    def clear_checkpoints(self) -> None:
+        for tset in (TSet.Train, TSet.Validation):
+            path = self.checkpoint_path(tset)
+            if os.path.exists(path):
+                os.remove(path)

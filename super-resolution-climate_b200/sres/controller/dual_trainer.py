@@ -26,7 +26,7 @@ from sres.data.tiles import TileIterator
 from sres.model.manager import SRModels
 from sres_b200 import _lib as L
 from sres_b200 import nn as _snn
-from sres_b200.parallel import gather_rows, shard_range
+from sres_b200.parallel import dp_schedule, gather_rows, shard_range
 
 TensorOrTensors = Union[Tensor, Sequence[Tensor]]
 
@@ -140,16 +140,16 @@ class ModelTrainer(object):
     def conform_to_product(self, prd: Tensor, tar: Tensor) -> Tensor:
         return tar  # the CUDA loss crops the target to the product's (H,W) itself (dual_trainer.py:200-203)
 
-    def single_product_loss(self, prd: Tensor, tar: Tensor) -> Tensor:
+    def single_product_loss(self, prd: Tensor, tar: Tensor, weight: float = 1.0) -> Tensor:
         fn = cfg().model.loss_fn
         if fn not in ("l2", "charbonnier", "l1"):
             raise Exception("Unknown single-product loss function {}".format(fn))
-        return _snn.loss(prd, tar, fn, self._loss_group())
+        return _snn.loss(prd, tar, fn, self._loss_group(), weight)
 
-    def loss(self, products: TensorOrTensors, target: Tensor) -> Tuple[float, Tensor]:
+    def loss(self, products: TensorOrTensors, target: Tensor, weight: float = 1.0) -> Tuple[float, Tensor]:
         """(python float, differentiable tensor) like dual_trainer.py:221-234 (`.item()` syncs)."""
         if isinstance(products, torch.Tensor):
-            sloss = self.single_product_loss(products, target)
+            sloss = self.single_product_loss(products, target, weight)
             return sloss.item(), sloss
         raise NotImplementedError("multi-scale product lists are not produced by RCAN")
 
@@ -179,7 +179,7 @@ class ModelTrainer(object):
             if self.rank == 0:
                 self.checkpoint_manager.clear_checkpoints()
         else:
-            self.train_state = self.checkpoint_manager.load_checkpoint(TSet.Train, update_model=True) or {}
+            self.train_state = self.checkpoint_manager.load_checkpoint(TSet.Train, update_model=True)
             epoch0 = self.train_state.get("epoch", 1)
             itime0 = self.train_state.get("itime", 0)
             epoch_loss = self.train_state.get("loss", float("inf"))
@@ -195,15 +195,16 @@ class ModelTrainer(object):
                 tile_iter = TileIterator.get_iterator(ntiles=timeslice.sizes["tiles"], randomize=True)
                 binput = boutput = btarget = None
                 batches = list(iter(tile_iter))
-                # data parallel: every global step consumes `world` consecutive batches of the shuffled order
-                for i0 in range(0, len(batches) - len(batches) % self.world, self.world):
-                    ctile = batches[i0 + self.rank]
+                # data parallel: every global step consumes `world` consecutive batches of the shuffled order; in a ragged
+                # last step the ranks without a batch re-run one with loss weight 0 (sres_b200.parallel.dp_schedule)
+                for ibatch, weight in dp_schedule(len(batches), self.rank, self.world):
+                    ctile = batches[ibatch]
                     batch_data = self.get_srbatch(ctile, ctime)
                     if batch_data is None:
                         break
                     self.optimizer.zero_grad()
                     binput, boutput, btarget = self.apply_network(batch_data)
-                    [sloss, mloss] = self.loss(boutput, btarget)
+                    [sloss, mloss] = self.loss(boutput, btarget, weight)
                     tile_iter.register_loss("model", sloss)
                     if interp_loss:
                         with torch.no_grad():
@@ -243,9 +244,6 @@ class ModelTrainer(object):
         torch.manual_seed(seed)
         if kwargs.get("update_model", False):
             self.train_state = self.checkpoint_manager.load_checkpoint(TSet.Validation, **kwargs)
-            if self.train_state is None:
-                print("Error loading checkpoint file, skipping evaluation.")
-                return {}, {}
         self.time_index = itime
         self._sync_python_rng()
         self.init_data_timestamps()

@@ -311,7 +311,7 @@ def bicubic_resize(t: torch.Tensor, scale_factor: float) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------
 class _LossFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, prd, tar, kind, process_group):
+    def forward(ctx, prd, tar, kind, process_group, weight):
         lib = L.lib()
         p = prd.detach().contiguous().float()
         t = tar.detach().contiguous().float()
@@ -328,35 +328,43 @@ class _LossFunction(torch.autograd.Function):
             st = L.cur_stream()
             L.check(lib.sres_loss_sum(L.ptr(p), L.ptr(t), B * Cc, H, W, tH, tW, kind, L.ptr(stat), L.ptr(ws),
                                       C.c_size_t(wsb), st), "sres_loss_sum")
-            n_total = float(p.numel())
+            if weight == 0.0:
+                stat.zero_()      # a rank that only keeps the collectives company (ragged last global step)
             if process_group is not None:
                 import torch.distributed as dist
-                dist.all_reduce(stat, group=process_group)  # global-batch loss
-                n_total *= dist.get_world_size(process_group)
-            L.check(lib.sres_loss_value(L.ptr(stat), C.c_double(n_total), kind, L.ptr(loss), st), "sres_loss_value")
-        ctx.save_for_backward(p, t, loss)
-        ctx.kind, ctx.n_total = kind, n_total
+                # global-batch loss: the sum AND the element count are reduced, so the ranks may hold
+                # batches of different sizes (the short last batch of a timeslice lands on an arbitrary rank)
+                dist.all_reduce(stat, group=process_group)
+            ntd = C.c_void_p(stat.data_ptr() + 8)
+            L.check(lib.sres_loss_value(L.ptr(stat), C.c_double(0.0), ntd, kind, L.ptr(loss), st), "sres_loss_value")
+        ctx.save_for_backward(p, t, loss, stat)
+        ctx.kind, ctx.weight = kind, float(weight)
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, gout):
-        p, t, loss = ctx.saved_tensors
+        p, t, loss, stat = ctx.saved_tensors
         B, Cc, H, W = p.shape
         grad = torch.empty_like(p)
         gs = gout.detach().reshape(1).to(device=p.device, dtype=torch.float32).contiguous()  # no host sync
         with torch.cuda.device(p.device):
             L.check(L.lib().sres_loss_grad(L.ptr(p), L.ptr(t), B * Cc, H, W, t.shape[2], t.shape[3], ctx.kind, L.ptr(loss),
-                                           C.c_double(ctx.n_total), C.c_float(1.0), L.ptr(gs), L.ptr(grad), L.cur_stream()),
+                                           C.c_double(0.0), C.c_void_p(stat.data_ptr() + 8), C.c_float(ctx.weight), L.ptr(gs),
+                                           L.ptr(grad), L.cur_stream()),
                     "sres_loss_grad")
-        return grad, None, None, None
+        return grad, None, None, None, None
 
 
-def loss(prd: torch.Tensor, tar: torch.Tensor, kind: str = "l2", process_group=None) -> torch.Tensor:
+def loss(prd: torch.Tensor, tar: torch.Tensor, kind: str = "l2", process_group=None, weight: float = 1.0) -> torch.Tensor:
     """Scalar loss on the CUDA kernels.  kind: 'l2' (RMSE over the whole batch tensor), 'charbonnier',
-    'l1'.  With a process group the loss (and therefore the gradient) is that of the GLOBAL batch."""
+    'l1'.  With a process group the loss (and therefore the gradient) is that of the GLOBAL batch: per-rank sums and
+    element counts are all-reduced, so ranks may hold batches of different sizes.  weight = 0 makes this rank a silent
+    participant (its batch adds nothing to the sum, the count or the gradient) -- see parallel.dp_schedule."""
     if prd.device.type != "cuda":
         raise L.SresError("sres_b200.loss needs CUDA tensors")
-    return _LossFunction.apply(prd, tar, LOSS_KINDS[kind], process_group)
+    if weight not in (0.0, 1.0):
+        raise ValueError("loss: weight must be 0 or 1")
+    return _LossFunction.apply(prd, tar, LOSS_KINDS[kind], process_group, float(weight))
 
 
 def l2loss(prd: torch.Tensor, tar: torch.Tensor, squared: bool = False) -> torch.Tensor:
@@ -408,13 +416,71 @@ class FusedAdam(torch.optim.Optimizer):
         else:
             self.model.engine.flat_grad.zero_()
 
+    # -- torch.optim.Adam's state_dict layout ------------------------------------------------------------------------
+    # {"state": {i: {"step", "exp_avg", "exp_avg_sq"}}, "param_groups": [{..., "params": [0..n-1]}]} with i the position of
+    # the parameter in model.parameters() -- what the reference's CheckpointManager saves and loads
+    # (sres/controller/checkpoints.py:20,44).  The flat moment buffers are cut along the engine's parameter layout.
+    def _adam_group_template(self) -> Dict[str, Any]:
+        probe = torch.optim.Adam([torch.zeros(1)], lr=1e-3)   # every key this torch version expects in a param group
+        return {k: v for k, v in probe.state_dict()["param_groups"][0].items() if k != "params"}
+
     def state_dict(self):
-        return dict(step=self.step_count, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq,
-                    param_groups=[{k: v for k, v in g.items() if k != "params"} for g in self.param_groups])
+        eng = self.model.engine
+        g = dict(self._adam_group_template())
+        g.update({k: v for k, v in self.param_groups[0].items() if k != "params"})
+        state, off = {}, 0
+        if self.step_count > 0:   # torch.optim.Adam has no per-parameter state before its first step
+            for i, (_, shape) in enumerate(eng.layout):
+                n = int(math.prod(shape))
+                state[i] = dict(step=torch.tensor(float(self.step_count)),
+                                exp_avg=self.exp_avg[off:off + n].view(shape).clone(),
+                                exp_avg_sq=self.exp_avg_sq[off:off + n].view(shape).clone())
+                off += n
+        g["params"] = list(range(len(eng.layout)))
+        return dict(state=state, param_groups=[g])
 
     def load_state_dict(self, sd):
-        self.step_count = int(sd["step"])
-        self.exp_avg.copy_(sd["exp_avg"])
-        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
-        for g, s in zip(self.param_groups, sd["param_groups"]):
-            g.update(s)
+        """Accepts torch.optim.Adam's layout (a reference checkpoint, or one of ours) and the flat private layout the
+        first round of this build wrote ({step, exp_avg, exp_avg_sq, param_groups}).  Everything is checked before
+        anything is modified."""
+        eng = self.model.engine
+        if "state" not in sd:   # round-1 private layout
+            if not {"step", "exp_avg", "exp_avg_sq"} <= set(sd):
+                raise ValueError("FusedAdam.load_state_dict: neither torch.optim.Adam's layout nor the flat layout")
+            if sd["exp_avg"].numel() != self.exp_avg.numel():
+                raise ValueError("FusedAdam.load_state_dict: flat moment buffers of another model")
+            step, m_src, v_src = int(sd["step"]), [sd["exp_avg"]], [sd["exp_avg_sq"]]
+            flat = True
+        else:
+            groups = sd["param_groups"]
+            if len(groups) != 1 or list(groups[0].get("params", [])) != list(range(len(eng.layout))):
+                raise ValueError("FusedAdam.load_state_dict: expected one param group over all "
+                                 f"{len(eng.layout)} parameters in model order")
+            if groups[0].get("amsgrad", False) or groups[0].get("maximize", False):
+                raise ValueError("FusedAdam.load_state_dict: amsgrad / maximize are not supported")
+            state = sd["state"]
+            flat, m_src, v_src, steps = False, [], [], set()
+            if state:
+                for i, (name, shape) in enumerate(eng.layout):
+                    st = state.get(i, state.get(str(i)))
+                    if st is None or tuple(st["exp_avg"].shape) != tuple(shape) or tuple(st["exp_avg_sq"].shape) != tuple(shape):
+                        raise ValueError(f"FusedAdam.load_state_dict: state of parameter {i} ({name}) is missing or has the wrong shape")
+                    m_src.append(st["exp_avg"]); v_src.append(st["exp_avg_sq"])
+                    steps.add(int(float(st["step"])))
+                if len(steps) != 1:
+                    raise ValueError("FusedAdam.load_state_dict: parameters carry different step counts")
+            step = steps.pop() if state else 0
+        with torch.no_grad():
+            if not m_src:
+                self.exp_avg.zero_(); self.exp_avg_sq.zero_()
+            elif flat:
+                self.exp_avg.copy_(m_src[0]); self.exp_avg_sq.copy_(v_src[0])
+            else:
+                off = 0
+                for (_, shape), m, v in zip(eng.layout, m_src, v_src):
+                    n = int(math.prod(shape))
+                    self.exp_avg[off:off + n].copy_(m.reshape(-1)); self.exp_avg_sq[off:off + n].copy_(v.reshape(-1))
+                    off += n
+        self.step_count = step
+        for g, saved in zip(self.param_groups, sd["param_groups"]):
+            g.update({k: v for k, v in saved.items() if k in ("lr", "betas", "eps", "weight_decay")})

@@ -18,6 +18,22 @@ def shard_range(n_items: int, rank: int, world: int):
     return start, start + base + (1 if rank < rem else 0)
 
 
+def dp_schedule(n_batches: int, rank: int, world: int):
+    """Which tile batch `rank` runs at every global step of a timeslice, and with which loss weight.
+
+    Every global step consumes `world` consecutive batches of the (shuffled) order; the last step of a timeslice may
+    have fewer than `world` batches left.  The ranks without a batch of their own still have to take part in the
+    loss and gradient collectives, so they re-run one of the step's batches with weight 0 (it then adds nothing to the
+    global sum, the global element count or the gradient) instead of dropping the trailing batches.  Returns a list
+    of (batch_index, weight) with the same length on every rank; over all ranks every batch appears exactly once
+    with weight 1."""
+    steps = []
+    for i0 in range(0, n_batches, world):
+        left = min(world, n_batches - i0)
+        steps.append((i0 + rank, 1.0) if rank < left else (i0 + rank % left, 0.0))
+    return steps
+
+
 def gather_rows(local: Optional[torch.Tensor], counts: Sequence[int], row_shape: Sequence[int], device, group=None) -> torch.Tensor:
     """Concatenate per-rank row blocks in rank order on every rank: rank r contributes `counts[r]` rows of shape
     `row_shape` (fp32; `local` may be None / empty when counts[rank] == 0).  One all_gather of blocks padded to the

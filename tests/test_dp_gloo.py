@@ -50,7 +50,7 @@ def _worker(rank, world, port, out_q):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from sres_b200.parallel import SegmentAllReduce, gather_ranges, gather_rows, shard_range
+        from sres_b200.parallel import SegmentAllReduce, dp_schedule, gather_ranges, gather_rows, shard_range
         eng = _StubEngine(rank)
         ddp = SegmentAllReduce(eng, None, average=False)
         ddp.backward(eng, None, None, accumulate=False)
@@ -68,13 +68,26 @@ def _worker(rank, world, port, out_q):
         dist.all_reduce(stat)
         rmse = float(torch.sqrt(stat / full.numel()))
         ok_loss = abs(rmse - float(torch.sqrt((full ** 2).mean()))) < 1e-12
-        # tile-batch sharding used by ModelTrainer.train: rank r takes batch i0 + r of every `world` consecutive ones
+        # tile-batch sharding used by ModelTrainer.train (ntiles % batch_size != 0 AND nbatches % world != 0: 101 tiles in
+        # batches of 7 = 15 batches, the last one short, and an odd batch left over for two ranks): every rank walks the
+        # same number of global steps, every batch is trained exactly once, the rank without a batch in the ragged last
+        # step rides along with weight 0
         batches = list(range(0, 101, 7))
-        mine = [batches[i0 + rank] for i0 in range(0, len(batches) - len(batches) % world, world)]
+        sched = dp_schedule(len(batches), rank, world)
         gathered = [None] * world
-        dist.all_gather_object(gathered, mine)
-        flat = sorted(b for part in gathered for b in part)
-        ok_shard = flat == batches[: len(batches) - len(batches) % world] and len(set(map(len, gathered))) == 1
+        dist.all_gather_object(gathered, sched)
+        live = sorted(i for part in gathered for i, w in part if w == 1.0)
+        ok_shard = live == list(range(len(batches))) and len(set(map(len, gathered))) == 1
+        ok_shard = ok_shard and all(0 <= i < len(batches) for part in gathered for i, _ in part)
+        ok_shard = ok_shard and sum(1 for part in gathered for _, w in part if w == 0.0) == (-len(batches)) % world
+        # global-batch RMSE with UNEQUAL per-rank batches: sum and element count are both reduced (weight-0 ranks add 0, 0)
+        sizes = [7 * 3, 3 * 3] + [0] * (world - 2)
+        vals = torch.randn(sum(sizes), generator=torch.Generator().manual_seed(5), dtype=torch.float64)
+        lo = sum(sizes[:rank])
+        mine_v = vals[lo:lo + sizes[rank]]
+        st2 = torch.stack([(mine_v ** 2).sum(), torch.tensor(float(mine_v.numel()), dtype=torch.float64)])
+        dist.all_reduce(st2)
+        ok_loss = ok_loss and abs(float(torch.sqrt(st2[0] / st2[1])) - float(torch.sqrt((vals ** 2).mean()))) < 1e-12
         # inference sharding: ranks hold contiguous tile ranges (uneven, one rank may be empty), gather restores tile order
         tiles = torch.arange(7 * 2 * 3 * 3, dtype=torch.float32).reshape(7, 2, 3, 3)
         s7, e7 = shard_range(7, rank, world)

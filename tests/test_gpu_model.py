@@ -265,6 +265,82 @@ def test_gradient_accumulation_and_stock_adam(dev):
     assert all(p.grad is not None for p in model.parameters())
 
 
+def test_fused_adam_state_interchanges_with_torch_adam(dev, tmp_path):
+    """FusedAdam.state_dict() has torch.optim.Adam's layout (what the reference's CheckpointManager saves,
+    checkpoints.py:20,44): a stock Adam loads it and continues exactly like FusedAdam does, and the other way round;
+    a state that does not fit raises before anything is modified."""
+    from sres_b200 import nn as snn
+    cfg = O.model_cfg(nlayers=1, nblocks=2)
+    sd0 = O.make_state_dict(cfg, 2, 2)
+    x = torch.randn(2, 2, 12, 12, device=dev)
+    tgt = torch.randn(2, 2, 48, 48, device=dev)
+
+    def run(model, opt, nsteps):
+        for _ in range(nsteps):
+            opt.zero_grad()
+            snn.loss(model(x.clone().requires_grad_(True)), tgt, "l2").backward()
+            opt.step()
+
+    a = _build(cfg, 2, dev); a.load_state_dict(sd0)
+    oa = snn.FusedAdam(a, lr=1e-3, weight_decay=1e-4)
+    run(a, oa, 3)
+    state = oa.state_dict()
+    ref_layout = torch.optim.Adam(a.parameters(), lr=1e-3).state_dict()
+    assert set(state) == {"state", "param_groups"} and set(state["param_groups"][0]) == set(ref_layout["param_groups"][0])
+    assert sorted(state["state"]) == list(range(len(list(a.parameters())))) and set(state["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+    torch.save(dict(model_state_dict=a.state_dict(), optimizer_state_dict=state), tmp_path / "ck.pt")
+    ck = torch.load(tmp_path / "ck.pt", map_location="cpu", weights_only=False)
+    # continue with FusedAdam (a), with a stock Adam restored from the file (b), and with FusedAdam restored from
+    # that stock Adam's own state_dict (c)
+    b = _build(cfg, 2, dev); b.load_state_dict(ck["model_state_dict"])
+    ob = torch.optim.Adam(b.parameters(), lr=1e-3, weight_decay=1e-4)
+    ob.load_state_dict(ck["optimizer_state_dict"])
+    c = _build(cfg, 2, dev); c.load_state_dict(ck["model_state_dict"])
+    oc = snn.FusedAdam(c, lr=5e-2)
+    oc.load_state_dict(ob.state_dict())
+    assert oc.step_count == 3 and oc.param_groups[0]["lr"] == 1e-3 and oc.param_groups[0]["weight_decay"] == 1e-4
+    run(a, oa, 2); run(b, ob, 2); run(c, oc, 2)
+    fa, fb, fc = a.engine.flat, b.engine.flat, c.engine.flat
+    # (c) is bit-identical; the stock Adam's update differs in the last bits, which the next bf16-operand forward/backward
+    # amplifies (ReLU-mask flips) to a fraction of a percent of the 1e-3 update
+    assert rel_l2(fb, fa) < 5e-4 and torch.equal(fc, fa)
+    # a fresh optimizer has no per-parameter state, like torch's
+    assert snn.FusedAdam(_build(cfg, 2, dev), lr=1e-3).state_dict()["state"] == {}
+    bad = oa.state_dict()
+    bad["state"][1]["exp_avg"] = torch.zeros(3)
+    before = oc.exp_avg.clone()
+    with pytest.raises(ValueError):
+        oc.load_state_dict(bad)
+    assert torch.equal(oc.exp_avg, before) and oc.step_count == 5
+
+
+def test_loss_weight_zero_is_a_silent_participant(dev):
+    """A rank without a batch of its own in a ragged last data-parallel step re-runs a batch with loss weight 0: its sum,
+    its element count and its gradient are exactly zero, so the all-reduced global-batch loss ignores it."""
+    import torch.distributed as dist
+    from sres_b200 import nn as snn
+    prd = torch.randn(3, 2, 16, 16, device=dev, requires_grad=True)
+    tar = torch.randn(3, 2, 16, 16, device=dev)
+    own = not dist.is_initialized()
+    if own:
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29591", rank=0, world_size=1)
+    try:
+        for kind in ("l2", "charbonnier", "l1"):
+            ref = snn.loss(prd, tar, kind)
+            full = snn.loss(prd, tar, kind, dist.group.WORLD, 1.0)
+            assert torch.equal(full, ref)
+            prd.grad = None
+            full.backward()
+            assert prd.grad.abs().sum() > 0
+    finally:
+        if own:
+            dist.destroy_process_group()
+    prd.grad = None
+    z = snn.loss(prd, tar, "l1", None, 0.0)      # no group: sum 0 over count 0
+    z.backward()
+    assert float(prd.grad.abs().sum()) == 0.0
+
+
 def test_loss_decreases_when_training(dev):
     from sres_b200 import nn as snn
     cfg = O.model_cfg(nlayers=2, nblocks=2)
