@@ -2,12 +2,14 @@
 """Benchmark of the RCAN hot path (BASELINE.json metric: RCAN train tiles/s, 48x48 2-ch, x4).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
-    python bench.py --impl reference [--gpus N] ...                # the reference's CPU path (oracle port)
+    python bench.py --impl reference [--gpus N] ...                # the reference's own CPU path (oracle/_ref, else the port)
     torchrun --nproc-per-node N ... bench.py --gpus N ...          # data parallel, one rank per GPU
 
 One step = one optimizer step of RCAN-full (10 groups x 20 RCABs, 64 features, reduction 16, x4) on a
 batch of 64 synthetic 2-channel 48x48 LR tiles per GPU: bicubic down of the HR batch, forward, RMSE
-loss, backward, fused Adam.  Prints ONE JSON line (rank 0).
+loss, backward, fused Adam.  Prints ONE JSON line (rank 0).  Besides the headline (BASELINE config 2 / 3) the line
+carries `infer_region` (config 4: tile extraction, batched forward, stitching of a 3000 x 17280 region, host images out)
+and `x8` (config 5: x8 upscaling of 4-channel 96 x 96 tiles); `--skip-extras` leaves them out.
 """
 import argparse
 import json
@@ -18,7 +20,8 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.join(ROOT, "super-resolution-climate_b200"))
+PKG = os.path.join(ROOT, "super-resolution-climate_b200")   # put on sys.path by the CUDA arm only: the reference arm imports the
+                                                            # reference's own `sres` package, which has the same name
 
 WORKLOAD = dict(nlayers=10, nblocks=20, nfeatures=64, cbottleneck=16, downscale_factors=[2, 2])
 TILE, CH, SCALE, BATCH = 48, 2, 4, 64
@@ -77,24 +80,66 @@ def synth_hr(B, C, S, seed):
 
 
 # ---------------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the oracle port of the reference's PyTorch CPU path
+# reference arm / CPU baseline: the reference's OWN code (oracle/_ref = byte-for-byte staged copy of its `sres`
+# package, oracle/make_ref.py) on the host cores; the oracle port only when no copy of the reference is around
 # ---------------------------------------------------------------------------------------------------
-def cpu_train_tiles_per_s(batch, steps, warmup, threads):
+CPU_WORKLOADS = {
+    # name: (model overrides, sample batch) -- BASELINE.md 5.3: RCAN-full on CPU is timed at batch 4..8
+    "full": (WORKLOAD, 8),
+    "config1": (dict(nlayers=4, nblocks=4, nfeatures=64, cbottleneck=16, downscale_factors=[2, 2]), 16),
+}
+
+
+def reference_step_fn(overrides, batch):
+    """(kind, step): one optimizer step of the reference's train loop body (dual_trainer.py:310-323 without logging)."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import rcan_oracle as O
-    torch.set_num_threads(threads)
-    cfg = O.model_cfg(**WORKLOAD)
+    import ref_import as R
+    cfg = O.model_cfg(**overrides)
+    hr = synth_hr(batch, CH, TILE * SCALE, 4456)
+    if R.available():
+        from synth import TASK
+        R.set_cfg(cfg, TASK)
+        import importlib
+        get_model = importlib.import_module(f"sres.model.{cfg['name']}.network").get_model      # manager.py:93-95
+        from sres.base.util import array as ref_array
+        from sres.controller.stats import l2loss as ref_l2
+        import sres.base.gpu as ref_gpu
+        ref_gpu.get_device = lambda: torch.device("cpu")
+        ref_array.get_device = ref_gpu.get_device
+        torch.manual_seed(4456)
+        model = get_model(nchannels_in=CH, nchannels_out=CH, device=torch.device("cpu"))
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=0.0)                      # dual_trainer.py:126
+
+        def step():
+            opt.zero_grad()
+            target = hr.clone().requires_grad_(True)        # array2tensor: requires_grad=True (array.py:70)
+            prd = model(ref_array.downsample(target))       # dual_trainer.py:569-570
+            loss = ref_l2(prd, target)
+            loss.backward()
+            opt.step()
+            return float(loss.item())
+        return "reference", step
     sd = O.make_state_dict(cfg, CH, CH)
     adam = O.AdamState(sd, lr=1e-4)
-    hr = synth_hr(batch, CH, TILE * SCALE, 4456)
+    return "port", (lambda: O.train_step(hr, sd, cfg, adam, "l2")[0])
+
+
+def cpu_train_tiles_per_s(which, steps, warmup, threads, budget_s=90.0):
+    import torch
+    torch.set_num_threads(threads)
+    overrides, batch = CPU_WORKLOADS[which]
+    kind, step = reference_step_fn(overrides, batch)
     for _ in range(warmup):
-        O.train_step(hr, sd, cfg, adam, "l2")
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        O.train_step(hr, sd, cfg, adam, "l2")
+        step()
+    t0, done = time.perf_counter(), 0
+    while done < steps and (done == 0 or time.perf_counter() - t0 < budget_s):
+        step()
+        done += 1
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps
+    return dict(kind=kind, batch=batch, steps=done, tiles_per_s=batch * done / dt, s_per_step=dt / done)
 
 
 def run_reference(args):
@@ -103,27 +148,153 @@ def run_reference(args):
         return
     import torch
     threads = os.cpu_count() or 1
-    batch = 2
-    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
-    tps, spstep = cpu_train_tiles_per_s(batch, steps, warmup, threads)
-    sample = f"{steps} timed steps of batch {batch} (of the {BATCH}-tile workload batch), fp32 PyTorch {torch.__version__} CPU, {threads} threads"
+    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
+    full = cpu_train_tiles_per_s("full", steps, warmup, threads, budget_s=60.0)
+    small = cpu_train_tiles_per_s("config1", min(steps, 5), 1, threads, budget_s=20.0) if not args.skip_extras else None
+    what = "the reference's own sres package (staged copy, oracle/_ref)" if full["kind"] == "reference" else "oracle port of the reference (no copy of the reference found)"
+    sample = (f"{full['steps']} timed steps of batch {full['batch']} (of the {BATCH}-tile workload batch), {what}, "
+              f"fp32 PyTorch {torch.__version__} CPU, {threads} threads")
     line = {
-        "impl": "reference", "metric": METRIC, "value": tps, "unit": "tiles/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "RCAN-full (10x20 RCAB, 64 feats, reduction 16) x4 train step, 2-ch 48x48 LR tiles; CPU sample batch 2",
+        "impl": "reference", "metric": METRIC, "value": full["tiles_per_s"], "unit": "tiles/s", "n_gpus": args.gpus,
+        "steps": full["steps"], "warmup": warmup, "ms_per_step": full["s_per_step"] * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"RCAN-full (10x20 RCAB, 64 feats, reduction 16) x4 train step, 2-ch 48x48 LR tiles; CPU sample batch {full['batch']}",
                    "tile": TILE, "channels": CH, "scale": SCALE, "batch_per_gpu": BATCH},
-        "cpu_baseline": {"value": tps, "unit": "tiles/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": tps, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {"value": full["tiles_per_s"], "unit": "tiles/s", "cores": threads, "kind": full["kind"], "sample": sample},
+        "e2e": {"value": full["tiles_per_s"], "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if small is not None:
+        line["config1"] = {"what": "BASELINE config 1: RCAN-small (4 groups x 4 RCABs, 64 feats) x4 train step, batch 16, CPU",
+                           "value": small["tiles_per_s"], "unit": "tiles/s", "ms_per_step": small["s_per_step"] * 1e3,
+                           "steps": small["steps"], "kind": small["kind"], "cores": threads}
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess():
+    """The reference arm in a fresh interpreter (this process has the product's `sres` mirror imported, the reference's
+    package has the same name).  Rank 0, N = 1 only."""
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1",
+                              "--skip-extras"], capture_output=True, text=True, timeout=600)
+        ref = json.loads(out.stdout.strip().splitlines()[-1])
+        return ref["cpu_baseline"]
+    except Exception as err:  # the baseline is reporting only: say what happened instead of failing the bench
+        return {"value": None, "unit": "tiles/s", "cores": os.cpu_count() or 1, "kind": "unavailable", "sample": f"reference arm failed: {err}"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE configs 4 and 5 (extra keys of the main line)
+# ---------------------------------------------------------------------------------------------------
+def bench_region(trainer, dev, world, rank, reps=3):
+    """Config 4 end to end through ModelTrainer.process_image: the (2, 3000, 17280) fp32 region starts in pinned HOST
+    memory; tile extraction + NaN-tile drop, lnorm, bicubic down, RCAN-full forward (no grad), de-normalise + stitch, and the
+    copy of the stitched images (input / target / interpolated / model of both variables) back to host memory are all
+    inside the timed region.  Under torchrun the tile batches are sharded over the ranks and gathered."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from sres.base.util.config import cfg
+    from sres.controller.config import TSet
+    from sres.data.batch import BatchDataset, synthetic_region
+    C_, Y, X = CH, 3000, 17280
+    region = torch.from_numpy(synthetic_region(C_, Y, X, seed=12)).pin_memory()
+    saved_order, saved_ds = cfg().task.get("tile_order", "reference"), trainer.model_manager._dataset
+    cfg().task["tile_order"] = "corrected"
+    trainer.model_manager._dataset = BatchDataset(region_source=lambda t: region.numpy())
+    trainer.model.eval()
+    times, ntiles, bytes_out = [], 0, 0
+    try:
+        for rep in range(reps + 1):          # rep 0 warms up (workspace, CUDA graph of the inference shape, pinned buffers)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            images, _ = trainer.process_image(TSet.Train, 0, ctime=rep)
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            if rep > 0:
+                times.append(float(dt.item()))
+            img = images[list(images)[0]]["model"]
+            ntiles = int(np.isfinite(img[::TILE * SCALE, ::TILE * SCALE]).sum())
+            bytes_out = sum(a.nbytes for v in images.values() for a in v.values())
+            del images, img
+    finally:
+        cfg().task["tile_order"] = saved_order
+        trainer.model_manager._dataset = saved_ds
+        trainer.model.train()
+    best = min(times)
+    mp = C_ * ntiles * (TILE * SCALE) ** 2 / 1e6
+    return {"what": "BASELINE config 4: process_image on a synthetic (2, 3000, 17280) region (15 x 90 grid of 192-px tiles, ~20 % land): "
+                    "extract, lnorm, bicubic down, RCAN-full forward, denorm + stitch, stitched images copied to host",
+            "value": mp / best, "unit": "output MP/s", "seconds": best, "seconds_all": times, "valid_tiles": ntiles, "variables": C_,
+            "h2d_bytes": int(region.numel() * 4), "d2h_bytes": int(bytes_out), "n_gpus": world,
+            "frac_of_tensor_peak": (C_ * ntiles / C_) / best * flops_per_tile(False) / 1e12 / world / peaks()["tflops_sustained"]}
+
+
+def bench_x8(dev, world, rank, steps, batch=8):
+    """Config 5: RCAN-full x8 (three PixelShuffle(2) stages) on 4-channel 96 x 96 LR tiles -> 768 x 768, one optimizer step
+    per step (bicubic down, forward, RMSE, backward, Adam), `batch` tiles per GPU."""
+    import torch
+    import torch.distributed as dist
+    from sres_b200 import nn as snn
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    C4, LR, SC = 4, 96, 8
+    torch.manual_seed(4456)
+    model = snn.RCAN(nchannels_in=C4, nchannels_out=C4, nfeatures=64, nlayers=WORKLOAD["nlayers"], nblocks=WORKLOAD["nblocks"],
+                     cbottleneck=WORKLOAD["cbottleneck"], scale=SC, device=dev)
+    group = None
+    if world > 1:
+        model.enable_data_parallel()
+        dist.broadcast(model.engine.flat, src=0)
+        model.engine.mark_params_changed()
+        group = dist.group.WORLD
+    opt = snn.FusedAdam(model, lr=1e-4)
+    hr = [synth_hr(batch, C4, LR * SC, 99 + 7 * rank + i).to(dev) for i in range(2)]
+
+    def step(i):
+        opt.zero_grad()
+        x = snn.bicubic_resize(hr[i % 2], 1.0 / SC)
+        loss = snn.loss(model(x.requires_grad_(True)), hr[i % 2], "l2", group)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        last = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    Fn, G, R, red = 64, WORKLOAD["nlayers"], WORKLOAD["nblocks"], WORKLOAD["cbottleneck"]
+    ups = sum(4 * Fn * Fn * 4 ** i for i in range(3))
+    fwd = 2 * 9 * LR * LR * (C4 * Fn + (G * (2 * R + 1) + 1) * Fn * Fn + ups + Fn * C4 * SC * SC) + G * R * 4 * Fn * Fn / red
+    tiles_s = world * batch / (ms / 1e3)
+    finite = bool(torch.isfinite(last).item())
+    del model, opt, hr
+    torch.cuda.empty_cache()
+    return {"what": f"BASELINE config 5: RCAN-full x8 train step on 4-channel 96x96 LR tiles (768x768 HR), batch {batch} per GPU",
+            "value": tiles_s, "unit": "tiles/s", "ms_per_step": ms, "batch_per_gpu": batch, "n_gpus": world, "loss_finite": finite,
+            "gflop_per_tile_train": 3 * fwd / 1e9,
+            "frac_of_tensor_peak": tiles_s / world * 3 * fwd / 1e12 / peaks()["tflops_sustained"]}
 
 
 # ---------------------------------------------------------------------------------------------------
 # this repo's arm
 # ---------------------------------------------------------------------------------------------------
 def run_cuda(args):
+    sys.path.insert(0, PKG)
     import torch
     import torch.distributed as dist
     from sres_b200 import _lib as L
@@ -249,20 +420,26 @@ def run_cuda(args):
     conv_flops = 2.0 * B * TILE * TILE * 64 * 64 * 9
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12
 
+    # ---- BASELINE configs 4 and 5 (all ranks take part) ------------------------------------------------
+    region = x8 = None
+    if not args.skip_extras:
+        del acts, outb
+        torch.cuda.empty_cache()
+        region = bench_region(trainer, dev, world, rank)
+        x8 = bench_x8(dev, world, rank, max(3, min(args.steps, 10)))
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- CPU baseline (oracle port) on a bounded sample ---------------------------------------------
+    # ---- CPU baseline: the reference arm on a bounded sample, host cores of this box (N = 1 only) -----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        tps, _ = cpu_train_tiles_per_s(2, 3, 1, threads)
-        cpu = {"value": tps, "unit": "tiles/s", "cores": threads, "kind": "port",
-               "sample": "3 timed steps of batch 2 of the same RCAN-full x4 train step (oracle/rcan_oracle.py, fp32 PyTorch CPU)"}
+        cpu = cpu_baseline_subprocess()
 
-    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of the same kernel/shape
+    # DRAM traffic of the dominant kernel: NOT measured in this run -- read from the committed `ncu --set full` capture of
+    # the same kernel and shape (profiles/r01_v4_conv_ncu_metrics.json; the kernel's data path has not changed since)
     traffic = None
     try:
         m = json.load(open(os.path.join(ROOT, "profiles", "r01_v4_conv_ncu_metrics.json")))
@@ -284,7 +461,7 @@ def run_cuda(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv3x3_igemm_kernel<64,false,17> (64->64 conv + bias + ReLU, bf16 out: RCAB conv1, B=64, 48x48)", "achieved": achieved,
                      "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_burst"], "traffic": traffic,
-                     "traffic_note": "DRAM bytes per launch (ncu --set full, profiles/r01_v4_conv_ncu_metrics.json); algorithmic 39.3 MB "
+                     "traffic_note": "from committed capture r01 (ncu --set full, profiles/r01_v4_conv_ncu_metrics.json), not measured in this run: DRAM bytes per launch; algorithmic 39.3 MB "
                                      "(19.7 in + 19.7 out): the input is read once, the output is still in L2 when the kernel ends",
                      "peak_source": pk["src"] + " burst (kernel timed alone)", "us_per_launch": conv_ms * 1e3,
                      "step_tflops_per_gpu": step_tflops, "step_frac_of_sustained": step_tflops / pk["tflops_sustained"]},
@@ -293,6 +470,9 @@ def run_cuda(args):
                       "what": "bicubic down + RCAN-full forward (no grad) on resident 64-tile batches, all GPUs",
                       "frac_of_tensor_peak": infer_tiles_s / world * flops_per_tile(False) / 1e12 / pk["tflops_sustained"]},
     }
+    if region is not None:
+        line["infer_region"] = region
+        line["x8"] = x8
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -305,6 +485,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true", help="leave out the config-4 / config-5 keys (and config 1 of the reference arm)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     if args.impl == "reference":

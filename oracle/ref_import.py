@@ -1,7 +1,8 @@
 """Import the UNMODIFIED reference (`/root/reference/sres`) in this container.
 
-TEST INFRASTRUCTURE ONLY -- used by oracle/gen_golden.py to pin the oracle; never imported by
-the product, by bench.py or by any test that runs on the GPU box (/root/reference is absent there).
+TEST / MEASUREMENT INFRASTRUCTURE ONLY -- used by oracle/gen_golden.py to pin the oracle and by the reference arm of
+bench.py (which, on the GPU box, finds the staged copy oracle/_ref made by oracle/make_ref.py); never imported by
+the product or by any test that runs on the GPU box.
 
 The reference needs hydra / omegaconf / xarray / parse / netCDF4 / matplotlib ..., none of which
 is installed here.  We register stub modules for exactly those third-party packages:
@@ -20,7 +21,16 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = "/root/reference"
+import os as _os
+
+# the reference tree in the build container, else the byte-for-byte staged copy (oracle/make_ref.py) that travels to
+# the GPU box for the reference arm of bench.py
+_STAGED = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "_ref")
+REFERENCE_ROOT = "/root/reference" if _os.path.isdir("/root/reference/sres") else _STAGED
+
+
+def available() -> bool:
+    return _os.path.isdir(_os.path.join(REFERENCE_ROOT, "sres"))
 _STUB_TOPLEVEL = ("hydra", "omegaconf", "xarray", "parse", "netCDF4", "matplotlib", "ipywidgets", "zarr", "dask",
                   "h5py", "nvidia", "IPython", "cartopy", "ipympl", "modulus", "cftime")
 
