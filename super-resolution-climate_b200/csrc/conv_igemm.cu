@@ -727,6 +727,12 @@ static int launch_conv(const sres_conv_args* a, cudaStream_t stream) {
     if ((a->epi_flags & (SRES_EPI_POOL | SRES_EPI_DOT)) && conv_n192_available(a->H, a->W) && !(a->debug_flags & (2 | 4 | 8 | 32 | 64)))
       return set_error(SRES_ERR_UNSUPPORTED, "conv: with SRES_CONV_N192=2 per-tile partial sums need the identity-mapped TMA epilogue with one output and no second addend");
   }
+  // tail convolution (16 packed output rows, planar output): the three-taps-per-MMA kernel's narrow variant; its halo
+  // staging does not grow with the image width (debug_flags bit 6 keeps the tap-per-MMA kernel)
+  if (a->n_out == 16 && a->out_nchw && a->map_mode == SRES_MAP_IDENT && !a->out_f32 && !a->out_bf16 && !a->resid_f32 &&
+      !a->resid2_f32 && !a->mask_bf16 && !(a->epi_flags & (SRES_EPI_POOL | SRES_EPI_DOT)) && a->c_real >= 1 && a->c_real <= 16 &&
+      !(a->debug_flags & (2 | 4 | 8 | 32 | 64)) && conv_n48_available(a->H, a->W))
+    return launch_conv_n48(a, stream);
   ConvKParams p{};
   p.B = a->B; p.H = a->H; p.W = a->W; p.P = a->W + 1; p.R = a->H + 1;
   const long long npos = (long long)p.B * p.R * p.P;
@@ -847,7 +853,7 @@ extern "C" int sres_conv_mtiles(int B, int H, int W) {
 }
 
 extern "C" int sres_conv_supported(int H, int W, int n_out) {
-  (void)H;
+  if (n_out == 16 && sres::conv_n48_available(H, W)) return 1;
   const int wbytes = 9 * n_out * 128;
   const int rows = 128 + 2 * (W + 2);
   const int stage_rows = (rows + sres::kBoxRows - 1) / sres::kBoxRows * sres::kBoxRows;

@@ -45,6 +45,8 @@ struct ConvN192Params {
   const float* bias;
   const uint16_t* mask;  // bf16 PTL: ReLU mask, or the second factor of SRES_EPI_DOT (read straight from global memory)
   float* part;           // [n_tiles][2][4][64] per-tile, per-image-segment channel sums (SRES_EPI_POOL / SRES_EPI_DOT)
+  float* out_nchw;       // narrow variant: planar fp32 output (B, c_real, H, W)
+  int c_real;
   int use_o16, use_msk, use_r32, use_o32;
   int off_s16, off_s32, off_xch, off_tail;
   long long* timeline;
@@ -123,7 +125,9 @@ constexpr int kNO16 = 1, kNO32 = 2, kNR32 = 4, kNMsk = 8, kNRelu = 16, kNPool = 
 // Group g drains accumulator stage g, i.e. every second tile of the CTA: the shifted sum costs 512 warp shuffles per
 // tile and the SM shuffles one warp per clock, so one group alone (drain, exchange, shuffle, store in sequence) needs
 // about 1700 cycles per tile against the 1164 the tensor pipe takes; two groups have two tile times each.
-template <int FL>
+// NB = output features per horizontal tap: 64 (N = 192, the trunk convolutions) or 16 (N = 48: the tail convolution
+// 64 -> Cout <= 16, planar fp32 output straight from registers, any image width -- BASELINE config 5's 768-pixel rows).
+template <int NB, int FL>
 __global__ void __launch_bounds__(kNThreads, 1)
 conv3x3_n192_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmO16a, const __grid_constant__ CUtensorMap tmO16b,
@@ -133,7 +137,8 @@ conv3x3_n192_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset arithmetic keeps LDS/STS
   uint8_t* smem_w = smem;
-  uint8_t* smem_a = smem + kNWBytes;
+  constexpr int kWRow = 3 * NB * 128;   // bytes of one kernel row of the packed weights (three taps)
+  uint8_t* smem_a = smem + 3 * kWRow;
   uint8_t* tail = smem + p.off_tail;
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(tail);  // [kNStages]
   uint64_t* bar_empty = bar_full + kNStages;                // [kNStages]
@@ -166,7 +171,7 @@ conv3x3_n192_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int i = 0; i < 3; ++i) mbar_init(&bar_w[i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_tfull[i], 1);
-      mbar_init(&bar_tempty[i], 8);  // one arrive per warp of the group that drains the stage
+      mbar_init(&bar_tempty[i], NB == 64 ? 8 : 4);  // one arrive per warp of the group that drains the stage
     }
     for (int i = 0; i < 16; ++i) mbar_init(&bar_in[i], 1);
     mbar_fence_init();
@@ -175,7 +180,7 @@ conv3x3_n192_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tmem_alloc(tmem_holder, 512);  // two accumulator stages of 192 columns, 256 apart
     tmem_relinquish();
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 128) s_bias[threadIdx.x - 64] = p.bias ? p.bias[threadIdx.x - 64] : 0.f;
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + NB) s_bias[threadIdx.x - 64] = p.bias ? p.bias[threadIdx.x - 64] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -188,8 +193,8 @@ conv3x3_n192_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool leader = elect_one();
     if (leader) {
       for (int ky = 0; ky < 3; ++ky) {   // one barrier per kernel row: the first MMAs start after a third of the weights
-        mbar_expect_tx(&bar_w[ky], 192 * 128);
-        tma_load_2d(smem_w + ky * 192 * 128, &tmW, &bar_w[ky], 0, ky * 192);
+        mbar_expect_tx(&bar_w[ky], kWRow);
+        tma_load_2d(smem_w + ky * kWRow, &tmW, &bar_w[ky], 0, ky * 3 * NB);
       }
     }
     pdl_wait();  // the packed weights are old; the activations come from the previous kernel
@@ -210,7 +215,7 @@ conv3x3_n192_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const bool leader = elect_one();
-    constexpr uint32_t idesc = make_idesc_bf16(128, 192, 0, 0);
+    constexpr uint32_t idesc = make_idesc_bf16(128, 3 * NB, 0, 0);
     constexpr uint32_t dhi = sdesc_hi_sw128(1024);
     const uint32_t w_lo = sdesc_lo(smem_u32(smem_w), 16);
     const uint32_t a_lo0 = sdesc_lo(smem_u32(smem_a), 16);
@@ -240,7 +245,7 @@ conv3x3_n192_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (leader) {
           const uint32_t a_row = a_tile + uint32_t(ky) * ky_step;
-          const uint32_t b_row = w_lo + uint32_t(ky * 192 * 8);
+          const uint32_t b_row = w_lo + uint32_t(ky * 3 * NB * 8);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             if (ky == 0 && k == 0) umma_bf16_lohi<false>(d_tmem, a_row, dhi, b_row, dhi, idesc);
@@ -256,6 +261,88 @@ conv3x3_n192_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       __syncwarp();
     }
     N192_STAMP(5);
+  } else if constexpr (NB == 16) {
+    // ===================== epilogue, narrow variant: 16 columns per tap, planar fp32 output =====================
+    const int ew = warp - 2;
+    const int grp = ew >> 3;
+    const int wq = warp & 3;
+    const int RP = p.R * p.P;
+    float* xch = reinterpret_cast<float*>(smem + p.off_xch) + grp * 512;
+    const int src_up = (lane + 31) & 31, src_dn = (lane + 1) & 31;
+    const bool f_relu = bool(p.flags & SRES_EPI_RELU);
+    pdl_wait();
+    if (((ew >> 2) & 1) == 0) {   // one warp per lane quarter and group; the other eight epilogue warps have nothing to do
+      for (int tile = blockIdx.x + grp * gridDim.x, it = grp; tile < p.n_tiles; tile += 2 * gridDim.x, it += 2) {
+        const uint32_t aph = (it >> 1) & 1;
+        const int tile_base = tile * kNTileOut;
+        const int i = wq * 32 + lane;
+        const int q = tile_base - 1 + i;
+        const bool own = i >= 1 && i <= kNTileOut && q < p.npos;
+        const int qc = own ? q : tile_base;
+        const int b = qc / RP;
+        const int rem = qc - b * RP;
+        const int y = rem / p.P;
+        const int x = rem - y * p.P;
+        const bool live = own && x != p.W && y != p.H;
+        mbar_wait(&bar_tfull[grp], aph, 5);
+        tc_fence_after();
+        uint32_t d0[16], d1[16], d2[16];
+        const uint32_t trow = tmem_base + (uint32_t(wq * 32) << 16) + uint32_t(grp * 256);
+        tmem_ld16(trow, d0);
+        tmem_ld16(trow + 16, d1);
+        tmem_ld16(trow + 32, d2);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_tempty[grp]);
+        float* xs = xch + (it & 2) * 128;   // two slots, alternating per tile of this group
+        if (lane == 31) {
+          float4* d = reinterpret_cast<float4*>(xs + (0 * 4 + wq) * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            d[j] = make_float4(__uint_as_float(d0[4 * j]), __uint_as_float(d0[4 * j + 1]), __uint_as_float(d0[4 * j + 2]),
+                               __uint_as_float(d0[4 * j + 3]));
+        }
+        if (lane == 0) {
+          float4* d = reinterpret_cast<float4*>(xs + (1 * 4 + wq) * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            d[j] = make_float4(__uint_as_float(d2[4 * j]), __uint_as_float(d2[4 * j + 1]), __uint_as_float(d2[4 * j + 2]),
+                               __uint_as_float(d2[4 * j + 3]));
+        }
+        named_bar_sync(1 + grp, 128);
+        if (lane == 31 && wq > 0) {
+          const float4* s4 = reinterpret_cast<const float4*>(xs + (0 * 4 + wq - 1) * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 t = s4[j];
+            d0[4 * j] = __float_as_uint(t.x); d0[4 * j + 1] = __float_as_uint(t.y);
+            d0[4 * j + 2] = __float_as_uint(t.z); d0[4 * j + 3] = __float_as_uint(t.w);
+          }
+        }
+        if (lane == 0 && wq < 3) {
+          const float4* s4 = reinterpret_cast<const float4*>(xs + (1 * 4 + wq + 1) * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 t = s4[j];
+            d2[4 * j] = __float_as_uint(t.x); d2[4 * j + 1] = __float_as_uint(t.y);
+            d2[4 * j + 2] = __float_as_uint(t.z); d2[4 * j + 3] = __float_as_uint(t.w);
+          }
+        }
+        __syncwarp();
+        float* dst = p.out_nchw + ((long long)b * p.c_real * p.H + y) * p.W + x;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          if (c < p.c_real) {   // warp-uniform: only the real output channels are shifted and stored
+            const float up = __uint_as_float(__shfl_sync(0xffffffffu, d0[c], src_up));
+            const float dn = __uint_as_float(__shfl_sync(0xffffffffu, d2[c], src_dn));
+            float v = ((__uint_as_float(d1[c]) + s_bias[c]) + up) + dn;
+            if (f_relu) v = fmaxf(v, 0.f);
+            if (live) dst[(long long)c * p.H * p.W] = v;   // consecutive lanes = consecutive pixels of a plane
+          }
+        }
+      }
+    }
   } else {
     // ===================== epilogue =====================
     const int ew = warp - 2;          // 0..15
@@ -332,8 +419,8 @@ conv3x3_n192_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int c0 = half * 32 + ch * 16;
         uint32_t d0[16], d1[16], d2[16];
         tmem_ld16(trow + ch * 16, d0);
-        tmem_ld16(trow + ch * 16 + 64, d1);
-        tmem_ld16(trow + ch * 16 + 128, d2);
+        tmem_ld16(trow + ch * 16 + NB, d1);
+        tmem_ld16(trow + ch * 16 + 2 * NB, d2);
         tmem_ld_wait();
         if (ch == 1) {  // accumulator stage drained: the tensor core may reuse it
           tc_fence_before();
@@ -493,7 +580,7 @@ struct N192Plan {
   int off_s16, off_s32, off_xch, off_tail;
   size_t smem;
 };
-static bool n192_plan(N192Plan* pl, int W, bool o16, bool f32slab) {
+static bool n192_plan(N192Plan* pl, int W, bool o16, bool f32slab, int wbytes = kNWBytes) {
   const int smem_max = 232448;  // 227 KB
   const int P = W + 1;
   const int window = 128 + 2 * P;   // union of the three kernel rows' 128-row blocks
@@ -507,11 +594,11 @@ static bool n192_plan(N192Plan* pl, int W, bool o16, bool f32slab) {
   }
   pl->stage_bytes = pl->nbox * pl->box_rows * 128;
   const int slab = (o16 ? 32768 : 0) + (f32slab ? 65536 : 0);   // one slab per epilogue warp, two groups of eight
-  int ns = (smem_max - 1024 - kNWBytes - slab - 4096 - 1024) / pl->stage_bytes;
+  int ns = (smem_max - 1024 - wbytes - slab - 4096 - 1024) / pl->stage_bytes;
   if (ns > kNStages) ns = kNStages;
   if (ns < 2) return false;
   pl->nstage = ns;
-  int off = kNWBytes + ns * pl->stage_bytes;
+  int off = wbytes + ns * pl->stage_bytes;
   pl->off_s16 = off; off += o16 ? 32768 : 0;
   pl->off_s32 = off; off += f32slab ? 65536 : 0;
   pl->off_xch = off; off += 4096;
@@ -597,11 +684,11 @@ int launch_conv_n192(const sres_conv_args* a, cudaStream_t stream) {
   {                                                                                                                      \
     static thread_local int attr_dev = -1;                                                                               \
     if (attr_dev != dev) {                                                                                               \
-      e = cudaFuncSetAttribute(conv3x3_n192_kernel<FLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);           \
+      e = cudaFuncSetAttribute(conv3x3_n192_kernel<64, FLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);           \
       if (e != cudaSuccess) return set_cuda_error(e, "conv: smem attribute");                                           \
       attr_dev = dev;                                                                                                    \
     }                                                                                                                    \
-    e = launch_n192(conv3x3_n192_kernel<FLV>, dim3(grid), pl.smem, stream, tmA, tmW, tmO16a, tmO16b, tmMsk, tmR32,       \
+    e = launch_n192(conv3x3_n192_kernel<64, FLV>, dim3(grid), pl.smem, stream, tmA, tmW, tmO16a, tmO16b, tmMsk, tmR32,       \
                     tmO32a, tmO32b, p);                                                                                  \
   }
   switch (fl) {
@@ -614,6 +701,52 @@ int launch_conv_n192(const sres_conv_args* a, cudaStream_t stream) {
     default: N192_CASE(-1) break;
   }
 #undef N192_CASE
+  if (e != cudaSuccess) return set_cuda_error(e, "conv: launch");
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "conv: launch");
+  return SRES_OK;
+}
+
+// tail convolution 64 -> c_real <= 16 (weights packed with 16 rows per tap), planar fp32 output, any image width
+bool conv_n48_available(int H, int W) {
+  (void)H;
+  N192Plan pl;
+  static const int on = [] { const char* e = getenv("SRES_CONV_N48"); return e ? atoi(e) : 1; }();
+  return on != 0 && n192_plan(&pl, W, false, false, 9 * 16 * 128);
+}
+
+int launch_conv_n48(const sres_conv_args* a, cudaStream_t stream) {
+  ConvN192Params p{};
+  p.H = a->H; p.W = a->W; p.P = a->W + 1; p.R = a->H + 1;
+  const long long npos = (long long)a->B * p.R * p.P;
+  if (npos > 0x7fff0000LL) return set_error(SRES_ERR_UNSUPPORTED, "conv: batch too large for 32-bit rows");
+  p.npos = (int)npos;
+  p.n_tiles = (p.npos + kNTileOut - 1) / kNTileOut;
+  p.flags = a->epi_flags; p.bias = a->bias; p.out_nchw = a->out_nchw; p.c_real = a->c_real;
+  p.timeline = (long long*)a->debug_timeline;
+  N192Plan pl;
+  if (!n192_plan(&pl, a->W, false, false, 9 * 16 * 128)) return set_error(SRES_ERR_UNSUPPORTED, "conv: no room for the halo ring");
+  p.nstage = pl.nstage; p.stage_bytes = pl.stage_bytes; p.nbox = pl.nbox; p.box_rows = pl.box_rows; p.box_step = pl.box_step;
+  p.ky_step16 = pl.ky_step16;
+  p.off_s16 = pl.off_s16; p.off_s32 = pl.off_s32; p.off_xch = pl.off_xch; p.off_tail = pl.off_tail;
+  CUtensorMap tmA, tmW;
+  int rc = make_tmap_rows64(&tmA, a->in_bf16, (uint64_t)p.npos, pl.box_rows);
+  if (rc) return rc;
+  rc = make_tmap_rows64(&tmW, a->wpack_bf16, 9 * 16, 48);
+  if (rc) return rc;
+  const int sms = device_sm_count();
+  if (sms <= 0) return set_error(SRES_ERR_NO_DEVICE, "conv: no CUDA device");
+  const int grid = p.n_tiles < sms ? p.n_tiles : sms;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static thread_local int attr_dev = -1;
+  cudaError_t e;
+  if (attr_dev != dev) {
+    e = cudaFuncSetAttribute(conv3x3_n192_kernel<16, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return set_cuda_error(e, "conv: smem attribute");
+    attr_dev = dev;
+  }
+  e = launch_n192(conv3x3_n192_kernel<16, -1>, dim3(grid), pl.smem, stream, tmA, tmW, tmA, tmA, tmA, tmA, tmA, tmA, p);
   if (e != cudaSuccess) return set_cuda_error(e, "conv: launch");
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "conv: launch");

@@ -58,6 +58,9 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 bool conv_n192_available(int H, int W);
 bool conv_n192_fits(const sres_conv_args* a);
 int launch_conv_n192(const sres_conv_args* a, cudaStream_t stream);
+// narrow variant (N = 48): tail convolution 64 -> c_real <= 16 with planar fp32 output, any image width
+bool conv_n48_available(int H, int W);
+int launch_conv_n48(const sres_conv_args* a, cudaStream_t stream);
 
 #define SRES_CHECK_LAUNCH(where)                                  \
   do {                                                            \

@@ -336,7 +336,8 @@ def test_tail_conv_cuda_core_path_and_wide_images(env):
     """64 -> Cs tail conv on CUDA cores (the path for images wider than the tensor-core halo window) and the
     support predicate that selects it."""
     L, lib, dev = env
-    assert lib.sres_conv_supported(192, 192, 16) == 1 and lib.sres_conv_supported(768, 768, 16) == 0
+    # the narrow three-taps-per-MMA kernel stages one 128-row block per kernel row, whatever the image width
+    assert lib.sres_conv_supported(192, 192, 16) == 1 and lib.sres_conv_supported(768, 768, 16) == 1
     assert lib.sres_conv_supported(48, 48, 64) == 1 and lib.sres_conv_supported(384, 384, 64) == 1
     for Cs, B, H, W in [(2, 2, 20, 24), (4, 1, 9, 130)]:
         u = bf16_round(torch.randn(B, 64, H, W))
@@ -346,6 +347,29 @@ def test_tail_conv_cuda_core_path_and_wide_images(env):
                                            ptr(out), L.cur_stream()), "small_out")
         torch.cuda.synchronize()
         assert rel_l2(out.cpu(), F.conv2d(u, wt, bt, padding=1)) < 1e-5
+
+
+@pytest.mark.parametrize("Cs,B,H,W", [(2, 3, 20, 24), (1, 2, 9, 9), (4, 1, 16, 12), (2, 2, 192, 192), (4, 1, 24, 768), (3, 1, 100, 130)])
+def test_tail_conv_tensor_cores_any_width(env, Cs, B, H, W):
+    """Tail conv 64 -> Cs on the tensor cores: the narrow (N = 48) three-taps-per-MMA kernel (default; union halo window
+    for narrow images, one 128-row block per kernel row for wide ones -- 768-pixel rows of BASELINE config 5 included)
+    against fp32 torch on the same bf16 operands, and against the tap-per-MMA N = 16 kernel where that one fits."""
+    L, lib, dev = env
+    u = bf16_round(torch.randn(B, 64, H, W))
+    wt, bt = bf16_round(torch.randn(Cs, 64, 3, 3) * 0.05), torch.randn(Cs)
+    ref = F.conv2d(u, wt, bt, padding=1)
+    up = to_ptl(u.to(dev), torch.bfloat16)
+    bias16 = torch.zeros(16, device=dev)
+    bias16[:Cs] = bt.to(dev)
+    wp = pack(lib, wt.to(dev), 0, 16)
+    out = torch.full((B, Cs, H, W), float("nan"), device=dev)
+    run_conv(lib, conv_args(in_bf16=up, wpack_bf16=wp, bias=bias16, out_nchw=out, c_real=Cs, B=B, H=H, W=W, n_out=16))
+    assert torch.isfinite(out).all() and rel_l2(out.cpu(), ref) < 2e-3
+    if W <= 400:
+        old = torch.full((B, Cs, H, W), float("nan"), device=dev)
+        run_conv(lib, conv_args(in_bf16=up, wpack_bf16=wp, bias=bias16, out_nchw=old, c_real=Cs, B=B, H=H, W=W, n_out=16,
+                                debug_flags=64))
+        assert rel_l2(out.cpu(), old.cpu()) < 1e-5
 
 
 @pytest.mark.parametrize("B,H,W,red", [(3, 20, 24, 2), (2, 48, 48, 16), (4, 7, 9, 4)])

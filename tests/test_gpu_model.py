@@ -120,11 +120,13 @@ def test_train_step_matches_oracle_and_golden(name, dev, golden_dir):
     assert rel_l2(prd2.cpu(), prd_o) < TOL
 
 
-def test_x8_wide_tiles_forward_and_backward_run(dev):
-    """BASELINE config 5 geometry (x8, 4 channels, 96x96 LR -> 768x768 HR) at batch 1: wider than the tensor-core
-    halo window at the last level, so the tail conv takes the CUDA-core path.  Checked against the oracle."""
+@pytest.mark.parametrize("nblocks", [1, 20])
+def test_x8_wide_tiles_forward_and_backward_run(dev, nblocks):
+    """BASELINE config 5 geometry (x8, 4 channels, 96x96 LR -> 768x768 HR) at batch 1, with one RCAB and with one FULL
+    residual group (20 RCABs + group conv, reduction 16): three PixelShuffle stages up to 768-pixel rows, where the tail
+    conv runs on the narrow three-taps-per-MMA kernel.  Output, loss and the full gradient against the oracle."""
     from sres_b200 import nn as snn
-    cfg = O.model_cfg(nlayers=1, nblocks=1, downscale_factors=[2, 2, 2])
+    cfg = O.model_cfg(nlayers=1, nblocks=nblocks, cbottleneck=16 if nblocks > 1 else 2, downscale_factors=[2, 2, 2])
     sd = O.make_state_dict(cfg, 4, 4)
     hr = synth_hr(1, 4, 768, smooth=True)
     loss_o, prd_o, grads_o = O.loss_and_grads(hr, sd, cfg, "l2")
