@@ -48,12 +48,13 @@ class CheckpointManager:
         print(f" *** SAVE {tset.name} checkpoint, loss={loss:.5f} ({interp_loss:.5f}), to {path}, dt={time.time() - started:.4f} sec")
         return path
 
-    def load_checkpoint(self, tset: TSet = TSet.Train, update_model: bool = False, **_ignored) -> Optional[Dict[str, Any]]:
+    def load_checkpoint(self, tset: TSet = TSet.Train, update_model: bool = False, quiet: bool = False, **_ignored) -> Optional[Dict[str, Any]]:
         """The training state {epoch, itime, loss} of the checkpoint, {} when there is no file yet.  With update_model the
         optimizer state and then the weights are restored; a file that does not fit raises CheckpointError."""
         path = self.checkpoint_path(tset)
         if not os.path.exists(path):
-            print(f"No checkpoint file found at '{path}': starting from scratch.")
+            if not quiet:
+                print(f"No checkpoint file found at '{path}': starting from scratch.")
             return {}
         state = torch.load(path, map_location="cpu", weights_only=False)
         if update_model:

@@ -82,6 +82,7 @@ class ModelTrainer(object):
         self.tile_index: int = -1
         self.validation_loss: float = float("inf")
         self.data_timestamps: Dict[TSet, List[int]] = {}
+        self.eval_history: Dict[TSet, List[Dict[str, float]]] = {}
         self.train_state = None
 
     # -- plumbing ----------------------------------------------------------------------------------
@@ -227,9 +228,13 @@ class ModelTrainer(object):
                     self.checkpoint_manager.save_checkpoint(epoch, itime, TSet.Train, epoch_loss, il)
             if self.scheduler is not None:
                 self.scheduler.step()
+            # epoch-end validation pass; a new best model loss writes the validation checkpoint (dual_trainer.py:333-338, 534-539)
+            self.record_eval(epoch, {TSet.Train: epoch_loss}, TSet.Validation)
+            self.model.train()
             itime0 = 0
         train_time = time.time() - train_start
         ntotal_params = sum(p.numel() for p in self.model.parameters() if p.requires_grad)
+        self.record_eval(nepochs, {}, TSet.Test)
         if self.rank == 0:
             print(f" -------> Training model with {ntotal_params} wts took {train_time/60:.2f} min.")
         self.current_losses = dict(prediction=epoch_loss)
@@ -336,11 +341,40 @@ class ModelTrainer(object):
         torch.cuda.current_stream().synchronize()
         return {k: v.numpy() for k, v in pending.items()}
 
+    def record_eval(self, epoch: int, losses: Dict[TSet, float], tset: TSet, **kwargs) -> Optional[Dict[str, float]]:
+        """Evaluate `tset` when the train/test split gives it any timeslices and log the result (dual_trainer.py:349-358;
+        the reference's CSV results accumulator is outside the hot path: the history is kept in memory)."""
+        if cfg().task.ttsplit.get(tset.value, 0.0) <= 0.0:
+            return None
+        self.init_data_timestamps()
+        if not self.data_timestamps.get(tset):
+            return None
+        saved_ti = self.time_index
+        self.time_index = -1            # every timeslice of the set
+        try:
+            _, eval_losses = self.evaluate(tset, update_model=False, epoch=epoch, keep_results=False, **kwargs)
+        finally:
+            self.time_index = saved_ti
+        self.eval_history.setdefault(tset, []).append(dict(epoch=epoch, **eval_losses, **{f"{k.value}_loss": v for k, v in losses.items()}))
+        if self.rank == 0 and kwargs.get("verbose", False):
+            print(f" --->> record {tset.name} eval[{epoch}]: eval_losses={eval_losses}, losses={losses}")
+        return eval_losses
+
     def evaluate(self, tset: TSet, **kwargs):
-        """Batched forward over the tiles of a validation/test timeslice (dual_trainer.py:482-543).
-        Returns (dict(input,target,model,interpolated) -> numpy (N,C,·,·), dict(model, interpolated))."""
+        """Batched forward over the tiles of the validation / test timeslices (dual_trainer.py:482-543).
+        Returns (dict(input,target,model,interpolated) -> numpy (N,C,·,·), dict(model, interpolated)).  For the validation
+        set a model loss below the best one so far writes the validation checkpoint (:534-539); the best-so-far comes
+        from that checkpoint's `loss` entry (update_checkpoint, default on), the model itself is only reloaded when
+        update_model is passed."""
         assert tset in [TSet.Validation, TSet.Test], f"Invalid tset in training evaluation: {tset.name}"
         self.time_index = kwargs.get("time_index", self.time_index)
+        epoch = kwargs.get("epoch", None)
+        update_checkpoint = kwargs.get("update_checkpoint", True)
+        if update_checkpoint:
+            state = self.checkpoint_manager.load_checkpoint(TSet.Validation, update_model=kwargs.get("update_model", False), quiet=True)
+            self.validation_loss = state.get("loss", float("inf"))
+            if epoch is None:
+                epoch = state.get("epoch", 0)
         self._sync_python_rng()
         self.init_data_timestamps()
         ml, il, res = [], [], dict(input=[], target=[], model=[], interpolated=[])
@@ -356,10 +390,16 @@ class ModelTrainer(object):
                         binterp = upsample(binput)
                         ml.append(self.loss(boutput, btarget)[0])
                         il.append(self.loss(binterp, btarget)[0])
-                        for k, v in zip(res.keys(), (binput, btarget, boutput, binterp)):
-                            res[k].append(v.detach())
+                        if kwargs.get("keep_results", True):
+                            for k, v in zip(res.keys(), (binput, btarget, boutput, binterp)):
+                                res[k].append(v.detach())
                     if self.time_index >= 0:
                         break
         results = {k: (torch.cat(v).cpu().numpy() if v else None) for k, v in res.items()}
         losses = dict(model=float(np.mean(ml)) if ml else float("nan"), interpolated=float(np.mean(il)) if il else float("nan"))
+        if tset == TSet.Validation and ml and self.time_index < 0:
+            if losses["model"] < self.validation_loss or self.validation_loss == 0.0:
+                if update_checkpoint and self.validation_loss > 0.0 and self.rank == 0:
+                    self.checkpoint_manager.save_checkpoint(epoch or 0, 0, TSet.Validation, losses["model"], losses["interpolated"])
+                self.validation_loss = losses["model"]
         return results, losses

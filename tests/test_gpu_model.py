@@ -543,6 +543,13 @@ def test_controller_api_train_and_infer(dev, tmp_path):
             assert set(images[v]) == {"input", "target", "interpolated", "model"}
             assert images[v]["target"].shape == (480 // 48 * 48, 480 // 48 * 48) and images[v]["input"].shape == (120, 120)
             assert np.isfinite(losses[v]["model"]) and losses[v]["interpolated"] > 0
+        # the epoch-end validation passes of train() kept a history and wrote the best-validation checkpoint
+        hist = tr.eval_history[TSet.Validation]
+        assert [h["epoch"] for h in hist] == [1, 1] and all(np.isfinite(h["model"]) for h in hist)
+        vpath = tr.checkpoint_manager.checkpoint_path(TSet.Validation)
+        assert os.path.exists(vpath)
+        vck = torch.load(vpath, map_location="cpu", weights_only=False)
+        assert abs(vck["loss"] - min(h["model"] for h in hist)) < 1e-9 and vck["loss"] == tr.validation_loss
         res, l2 = tr.evaluate(TSet.Validation, time_index=0)
         assert res["model"].shape[1:] == (2, 48, 48) and np.isfinite(l2["model"])
     finally:
