@@ -311,6 +311,24 @@ SRES_API int sres_tiles_lnorm(const float* in, int nplanes, int T, int flip_inde
 SRES_API int sres_tiles_stitch(const float* tiles, int C, int ivar, int t, int gy, int gx, const int32_t* cell_to_tile,
                                const float* mean, const float* std_, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Raw LLC4320 fields -> region of interest (the reference's file reader)  */
+/*   sres/base/source/swot/raw.py:133-145 load_file: big-endian f4 ocean-only ("shrunk") file,  */
+/*   scattered through the template's land mask (template != 0), land = NaN, LLC faces unfolded */
+/*   by mds2d (sres/base/source/swot/util.py:3-55) into (3 nx, 4 nx), cropped by subset_roi      */
+/*   (raw.py:38-45).  The template is digested once into a gather index of the region; a file   */
+/*   then costs one host->device copy of its bytes and one gather kernel.                       */
+/* ------------------------------------------------------------------------------------------ */
+SRES_API size_t sres_llc_index_workspace_bytes(int nx);
+/* template_be: the 13 nx^2 big-endian floats of the template file, on the device (raw bytes).
+ * roi_index [ys*xs] int32: position of the pixel's value in a shrunk file, -1 for land.
+ * n_ocean_dev: device int64, number of ocean points = number of floats a shrunk file holds.     */
+SRES_API int sres_llc_build_roi_index(const void* template_be, int nx, int y0, int ys, int x0, int xs, void* workspace,
+                                      size_t workspace_bytes, int32_t* roi_index, int64_t* n_ocean_dev, void* stream);
+/* data_be: the n_data big-endian floats of one shrunk file, on the device (raw bytes); out [npix] fp32. */
+SRES_API int sres_llc_gather_roi(const void* data_be, int64_t n_data, const int32_t* roi_index, int64_t npix, float* out,
+                                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

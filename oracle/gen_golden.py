@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import ref_import as R  # noqa: E402
 import rcan_oracle as O  # noqa: E402
-from synth import MODEL_CASES, TASK, TILE_CASES, golden_file, sha, synth_hr, synth_region  # noqa: E402
+from synth import LLC_CASES, MODEL_CASES, TASK, TILE_CASES, golden_file, sha, synth_hr, synth_llc_files, synth_region  # noqa: E402
 
 GOLD = os.path.join(HERE, "..", "tests", "golden")
 
@@ -158,9 +158,42 @@ def gen_tiles_case(name, C, Y, X, tile, scale, seed, same_mask):
     print(f"tiles_{name}: tiles{tuple(ts.shape)} grid={ts.attrs['grid_shape']} ids[:6]={ts.coords['tiles'].values[:6]}")
 
 
+def gen_llc_case(name, nx, roi, seed, land):
+    """The reference's file reader on synthetic LLC files: load_file's own lines (raw.py:136-143) around the reference's
+    mds2d (called with the small test grid size; load_file itself hard-codes the default nx = 4320) and subset_roi."""
+    import tempfile
+    task = dict(TASK, name="golden", dataset="synthetic")
+    with tempfile.TemporaryDirectory() as tmp:
+        files = synth_llc_files(tmp, nx, seed, land)
+        R.set_cfg(O.model_cfg(), task, dataset=dict(files, roi=roi) if roi is not None else dict(files), platform=dict(cache=tmp))
+        from sres.base.source.swot.raw import filepath, subset_roi, template
+        from sres.base.source.swot.util import mds2d
+        from sres.base.util.config import cfg as ref_cfg
+        out = {}
+        for v in range(2):
+            for t in (3, 4):
+                for cparm, value in dict(varname=f"V{v}", index=t).items():          # raw.py:134-135
+                    ref_cfg().dataset[cparm] = value
+                path = filepath().replace("${dataset.varname}", f"V{v}").replace("${dataset.index}", str(t))
+                var_template = np.fromfile(template(), ">f4")
+                var_data = np.fromfile(path, ">f4")
+                mask = (var_template != 0)
+                var_template[mask] = var_data
+                var_template[~mask] = np.nan
+                sss_east, sss_west = mds2d(var_template, nx)
+                result = np.expand_dims(np.c_[sss_east, sss_west.T[::-1, :]], 0)
+                roi_data = subset_roi(result)
+                out[f"sha_V{v}_{t}"] = sha(np.ascontiguousarray(roi_data))
+                out[f"shape_V{v}_{t}"] = np.array(roi_data.shape)
+                out[f"nan_V{v}_{t}"] = np.int64(np.isnan(roi_data).sum())
+        out["sample"] = np.ascontiguousarray(roi_data[0, ::5, ::7])
+        np.savez_compressed(os.path.join(GOLD, f"llc_{name}.npz"), **out)
+        print(f"llc_{name}: roi{tuple(roi_data.shape)} nan={int(np.isnan(roi_data).sum())}")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["model", "tiles"]   # e.g. `gen_golden.py model edsr_tiny_x4` regenerates one model case
+    which = sys.argv[1:] or ["model", "tiles", "llc"]   # e.g. `gen_golden.py model edsr_tiny_x4` regenerates one model case
     if "model" in which:
         only = [a for a in which if a in MODEL_CASES]
         for name, case in MODEL_CASES.items():
@@ -169,6 +202,9 @@ def main():
     if "tiles" in which:
         for name, case in TILE_CASES.items():
             gen_tiles_case(name, *case)
+    if "llc" in which:
+        for name, case in LLC_CASES.items():
+            gen_llc_case(name, *case)
 
 
 if __name__ == "__main__":

@@ -81,3 +81,34 @@ TILE_CASES = {
 }
 
 
+
+
+LLC_CASES = {
+    # name: (nx, roi, seed, land fraction)
+    "nx24_roi": (24, dict(y0=13, ys=40, x0=5, xs=81), 21, 0.3),
+    "nx16_full": (16, None, 22, 0.5),
+    "nx40_west": (40, dict(y0=0, ys=120, x0=70, xs=90), 23, 0.1),
+}
+
+
+def synth_llc_files(folder, nx, seed, land_fraction, nvars=2, ntimes=2):
+    """Write a template (hFacC-like: 0 on land, a positive fraction on ocean, a few -0.0 land points) and
+    ocean-only big-endian float32 data files `raw/V{v}/V{v}.000{t}.shrunk` like config/dataset/swot_*.yaml names them."""
+    import os
+    rng = np.random.default_rng(seed)
+    n = 13 * nx * nx
+    tmpl = rng.random(n, dtype=np.float32) * 0.9 + 0.1
+    land = rng.random(n) < land_fraction
+    tmpl[land] = 0.0
+    tmpl[np.nonzero(land)[0][::7]] = -0.0          # negative zero is land too (template != 0 is False)
+    os.makedirs(os.path.join(folder, "meta"), exist_ok=True)
+    tmpl.astype(">f4").tofile(os.path.join(folder, "meta", "hFacC_k0.data"))
+    nocean = int((tmpl != 0).sum())
+    for v in range(nvars):
+        os.makedirs(os.path.join(folder, "raw", f"V{v}"), exist_ok=True)
+        for t in range(ntimes):
+            data = (rng.standard_normal(nocean).astype(np.float32) * 3.0 + 20.0 * (v + 1))
+            data[::11] = np.float32("nan")                      # missing values inside the ocean stay NaN
+            data.astype(">f4").tofile(os.path.join(folder, "raw", f"V{v}", f"V{v}.000{t + 3}.shrunk"))
+    return dict(dataset_root=folder, dataset_files="raw/${dataset.varname}/${dataset.varname}.000${dataset.index}.shrunk",
+                template="meta/hFacC_k0.data", nocean=nocean)

@@ -131,3 +131,30 @@ def assemble_images(batches: List[Dict[str, np.ndarray]], ivar: int, tile_ids: n
             tidx0 += batch.shape[0]
         out[image_type] = np.block(grid)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# raw LLC4320 reader (sres/base/source/swot/raw.py:133-145, :38-45; sres/base/source/swot/util.py:3-55)
+# ------------------------------------------------------------------------------------------------
+def llc_rearrange(d: np.ndarray, nx: int):
+    """util.py:3-7: faces 1-3 | faces 4-6 side by side (east), faces 8-13 (west); face 7 (Arctic) is dropped."""
+    deast = np.c_[d[:nx * nx * 3].reshape(3 * nx, nx), d[nx * nx * 3:nx * nx * 6].reshape(3 * nx, nx)]
+    dwest = d[nx * nx * 7:].reshape(nx * 2, nx * 3)
+    return deast, dwest
+
+
+def llc_load_file(template_path: str, data_path: str, nx: int, roi=None) -> np.ndarray:
+    """raw.py:133-145 with the grid size as a parameter (the reference hard-codes mds2d's default nx = 4320) and
+    subset_roi (raw.py:38-45) applied: (1, ys, xs) float32."""
+    var_template = np.fromfile(template_path, ">f4")
+    var_data = np.fromfile(data_path, ">f4")
+    mask = (var_template != 0)
+    var_template[mask] = var_data
+    var_template[~mask] = np.nan
+    east, west = llc_rearrange(var_template, nx)
+    result = np.expand_dims(np.c_[east, west.T[::-1, :]], 0)
+    if roi is not None:
+        x0, xs = roi.get("x0", 0), roi.get("xs", result.shape[-1])
+        y0, ys = roi.get("y0", 0), roi.get("ys", result.shape[-2])
+        result = result[..., y0:y0 + ys, x0:x0 + xs]
+    return result

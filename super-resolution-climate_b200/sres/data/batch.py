@@ -98,16 +98,31 @@ class BatchDataset(object):
         self.lib = L.lib()
 
     # -- regions ---------------------------------------------------------------------------------
+    def _llc_reader(self):
+        """`dataset.source: llc4320`: the raw LLC4320 files of config/dataset/swot_*.yaml (sres/data/llc4320.py)."""
+        if getattr(self, "_llc", None) is None:
+            from sres.data.llc4320 import LLC4320Reader
+            ds = cfg().dataset
+            self._llc = LLC4320Reader(str(ds.dataset_root), str(ds.dataset_files), str(ds.template), ds.get("roi", None),
+                                      int(ds.get("nx", 4320)), get_device())
+        return self._llc
+
     def get_dset_time_indices(self) -> List[int]:
+        if self.region_source is None and cfg().dataset.get("source", "synthetic") == "llc4320":
+            return self._llc_reader().time_indices(self.varnames[0])
         return list(range(int(cfg().dataset.get("ntimes", 1))))
 
-    def load_region_data(self, time_index: int, **kwargs) -> np.ndarray:
+    def load_region_data(self, time_index: int, **kwargs):
+        """(C,Y,X) float32 region of a time index: a host array, or a device tensor when the source already lives there."""
         if self.region_source is not None:
-            return np.ascontiguousarray(self.region_source(time_index), dtype=np.float32)
+            reg = self.region_source(time_index)
+            return reg if isinstance(reg, torch.Tensor) else np.ascontiguousarray(reg, dtype=np.float32)
         ds = cfg().dataset
+        if ds.get("source", "synthetic") == "llc4320":
+            return self._llc_reader().load_region_data(self.varnames, time_index)
         if ds.get("source", "synthetic") != "synthetic":
-            raise NotImplementedError("sres (B200 build): only `dataset.source: synthetic` or a region_source callable "
-                                      "is available; the LLC4320 file reader is out of scope")
+            raise NotImplementedError(f"sres (B200 build): dataset.source '{ds.get('source')}' -- use synthetic, llc4320 or a "
+                                      "region_source callable")
         return synthetic_region(len(self.varnames), int(ds.region["ys"]), int(ds.region["xs"]),
                                 int(ds.get("seed", 0)) + 1000 * int(time_index), float(ds.get("nan_fraction", 0.2)))
 
@@ -140,7 +155,9 @@ class BatchDataset(object):
 
     def load_timeslice(self, time_index: int, **kwargs) -> TileArray:
         if time_index != self.time_index:
-            region = torch.from_numpy(self.load_region_data(time_index)).to(get_device(), non_blocking=True)
+            region = self.load_region_data(time_index)
+            region = (region if isinstance(region, torch.Tensor) else torch.from_numpy(region)).to(get_device(), non_blocking=True)
+            region = region.contiguous().float()
             self.timeslice = self.get_tiles(region)
             self.time_index = time_index
         return self.timeslice

@@ -70,6 +70,13 @@ class SegmentAllReduce:
         self.on_gpu = torch.device(engine.device).type == "cuda"
         self.comm_stream = torch.cuda.Stream(device=engine.device) if self.on_gpu else None
         self.segments = [engine.segment_params(s) for s in range(engine.num_segments())]
+        self.trace = None   # development aid (tools/dp_timeline.py): list of (label, stream name, event) when not None
+
+    def _mark(self, label, stream, name):
+        if self.trace is not None and self.on_gpu:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            self.trace.append((label, name, ev))
 
     def _reduce(self, engine, off, cnt):
         bucket = engine.flat_grad[off:off + cnt]
@@ -83,16 +90,21 @@ class SegmentAllReduce:
         if accumulate:
             raise RuntimeError("data-parallel backward needs fresh gradients (optimizer.zero_grad() each step)")
         main = torch.cuda.current_stream(engine.device) if self.on_gpu else None
+        self._mark("bwd begin", main, "main")
         for seg, (off, cnt) in enumerate(self.segments):
             engine.backward(xin, dout, accumulate=False, seg_begin=seg, seg_end=seg + 1)
             if self.on_gpu:
                 ev = torch.cuda.Event()
                 ev.record(main)
+                self._mark(f"seg {seg} done", main, "main")
                 with torch.cuda.stream(self.comm_stream):
                     self.comm_stream.wait_event(ev)
+                    self._mark(f"ar {seg} begin", self.comm_stream, "comm")
                     self._reduce(engine, off, cnt)
+                    self._mark(f"ar {seg} end", self.comm_stream, "comm")
             else:  # host-side logic only (gloo tests)
                 self._reduce(engine, off, cnt)
         if self.on_gpu:
             main.wait_stream(self.comm_stream)
+            self._mark("bwd joined", main, "main")
         engine.launches += engine.launches_backward()

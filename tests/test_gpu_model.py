@@ -513,6 +513,59 @@ def test_full_size_region_roundtrip(dev):
         ConfigContext.deactivate()
 
 
+def test_llc4320_reader_bit_exact(dev, golden_dir, tmp_path):
+    """The raw LLC4320 reader (pinned staging, gather index of the region built once from the template, one gather kernel per
+    file) returns bit for bit what the reference's load_file + subset_roi return: against the oracle on the same files and
+    against the reference's hashes, including -0.0 land points, NaNs inside the ocean, a region in the transposed / flipped
+    western faces, time-index discovery and a data file that does not match the template."""
+    from synth import LLC_CASES, synth_llc_files
+    from sres.data.llc4320 import LLC4320Reader
+    for name, (nx, roi, seed, land) in LLC_CASES.items():
+        gold = np.load(os.path.join(golden_dir, f"llc_{name}.npz"))
+        folder = str(tmp_path / name)
+        files = synth_llc_files(folder, nx, seed, land)
+        rd = LLC4320Reader(files["dataset_root"], files["dataset_files"], files["template"], roi, nx=nx, device=dev)
+        assert rd.time_indices("V0") == [3, 4] and rd.time_indices("V1") == [3, 4]
+        for v in range(2):
+            for t in (3, 4):
+                got = rd.load_file(f"V{v}", t).cpu().numpy()
+                ref = T.llc_load_file(os.path.join(folder, files["template"]), rd.file_path(f"V{v}", t), nx, roi)
+                assert got.shape == ref.shape and sha(got) == sha(np.ascontiguousarray(ref)) == str(gold[f"sha_V{v}_{t}"])
+        assert rd.n_ocean == files["nocean"]
+        reg = rd.load_region_data(["V0", "V1"], 4)
+        assert reg.shape == (2,) + got.shape[1:] and sha(reg[1:].cpu().numpy()) == str(gold["sha_V1_4"])
+        with open(rd.file_path("V0", 3), "ab") as fh:
+            fh.write(b"\0\0\0\0")
+        with pytest.raises(ValueError):
+            rd.load_file("V0", 3)
+
+
+def test_llc4320_source_feeds_the_tile_loader(dev, tmp_path):
+    """`dataset.source: llc4320` through the mirrored BatchDataset: time indices from the files, tiles cut from the region the
+    reader returns (device-resident end to end) equal the oracle's tiles of the oracle-read region."""
+    from synth import synth_llc_files
+    from sres.base.util.config import ConfigContext
+    from sres.data.batch import BatchDataset
+    nx, roi = 40, dict(y0=8, ys=100, x0=3, xs=150)
+    files = synth_llc_files(str(tmp_path), nx, 31, 0.02, nvars=1)
+    ConfigContext.deactivate()
+    ConfigContext.set_defaults(task="SST-tiles-48", dataset="synthetic_1200", platform="local")
+    ConfigContext.activate_global("sres", model="rcan-10-20-64", **{
+        "task.tile_size": dict(x=12, y=12), "task.input_variables": dict(V0="v"), "task.target_variables": ["V0"],
+        "dataset.source": "llc4320", "dataset.dataset_root": files["dataset_root"], "dataset.dataset_files": files["dataset_files"],
+        "dataset.template": files["template"], "dataset.roi": roi, "dataset.nx": nx})
+    try:
+        ds = BatchDataset()
+        assert ds.get_dset_time_indices() == [3, 4]
+        ts = ds.load_timeslice(4)
+        ref = T.llc_load_file(os.path.join(str(tmp_path), files["template"]), os.path.join(str(tmp_path), "raw/V0/V0.0004.shrunk"), nx, roi)
+        tiles_o, ids_o, gs_o = T.get_tiles([ref], dict(x=12, y=12), 4)
+        assert ts.attrs["grid_shape"] == gs_o and sha(ts.values) == sha(tiles_o)
+        np.testing.assert_array_equal(ts.coords["tiles"], ids_o)
+    finally:
+        ConfigContext.deactivate()
+
+
 # ------------------------------------------------------------------------------------------------
 # the mirror of the reference controller API, end to end
 # ------------------------------------------------------------------------------------------------

@@ -116,3 +116,21 @@ def test_flops_formula():
     assert abs(O.flops_per_tile(O.model_cfg(nlayers=4, nblocks=4), 2, 2) / 1e9 - 9.773) < 0.001
     n = sum(int(np.prod(s)) for s in O.param_shapes(cfg, 2, 2).values())
     assert n == 16313602 and len(O.param_shapes(cfg, 2, 2)) == 1630
+
+
+def test_llc_reader_oracle_matches_reference(golden_dir, tmp_path):
+    """oracle/tiles_oracle.py:llc_load_file (restatement of raw.py:133-145 + util.py:3-55 + subset_roi) against the hashes the
+    reference's own mds2d / subset_roi produced on the same seeded synthetic LLC files (oracle/gen_golden.py:gen_llc_case)."""
+    import tiles_oracle as T
+    from synth import LLC_CASES, sha, synth_llc_files
+    for name, (nx, roi, seed, land) in LLC_CASES.items():
+        gold = np.load(os.path.join(golden_dir, f"llc_{name}.npz"))
+        folder = str(tmp_path / name)
+        files = synth_llc_files(folder, nx, seed, land)
+        for v in range(2):
+            for t in (3, 4):
+                data = os.path.join(folder, "raw", f"V{v}", f"V{v}.000{t}.shrunk")
+                got = T.llc_load_file(os.path.join(folder, files["template"]), data, nx, roi)
+                assert list(got.shape) == list(gold[f"shape_V{v}_{t}"]) and got.dtype == np.float32
+                assert int(np.isnan(got).sum()) == int(gold[f"nan_V{v}_{t}"])
+                assert sha(np.ascontiguousarray(got)) == str(gold[f"sha_V{v}_{t}"])
