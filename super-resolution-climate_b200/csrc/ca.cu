@@ -341,9 +341,14 @@ ca_param_prep_kernel(const CaParamBatch batch, int B, int hid, float* __restrict
   }
 }
 
-// pass 2: one block per layer: outer-product sums over the batch in a fixed order (deterministic)
+// pass 2: one block per layer: outer-product sums over the batch in a fixed order (deterministic).  The per-image vectors
+// (dz, h, dh from pass 1 and the pooled mean) are staged in shared memory chunk by chunk with fully parallel, coalesced loads;
+// the sums then run out of shared memory.  (The first version walked the batch with dependent global loads: 69 us per
+// launch for 20 blocks, 0.7 ms per training step.)
+constexpr int kCaParamChunk = 32;   // images per shared-memory chunk: 32 x 256 floats = 32 KB
 __global__ void __launch_bounds__(kCaThreads)
 ca_param_sum_kernel(const CaParamBatch batch, int B, int hid, const float* __restrict__ scratch, int accumulate) {
+  __shared__ float sm[kCaParamChunk][4][64];   // [image][dz | h | dh | mean][64]
   const int layer = blockIdx.x, tid = threadIdx.x;
   const long long o = (long long)layer * batch.layer_stride;
   float* dw1 = batch.grads + o;
@@ -355,22 +360,31 @@ ca_param_sum_kernel(const CaParamBatch batch, int B, int hid, const float* __res
 #pragma unroll
   for (int i = 0; i < 16; ++i) a1[i] = a2[i] = 0.f;
   float ab1 = 0.f, ab2 = 0.f;
-  for (int b = 0; b < B; ++b) {
-    const float* sc = scratch + ((size_t)layer * B + b) * (64 + 2 * kCaMaxHidden);
-    const float* dz = sc;
-    const float* h = sc + 64;
-    const float* dh = sc + 64 + kCaMaxHidden;
-    const float* m = batch.mean + ((size_t)layer * B + b) * 64;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int e = tid + i * kCaThreads;
-      if (e < n12) {
-        a1[i] = fmaf(__ldg(dh + e / 64), __ldg(m + e % 64), a1[i]);    // dw1[j][c] = dh[j] * m[c]
-        a2[i] = fmaf(__ldg(dz + e / hid), __ldg(h + e % hid), a2[i]);  // dw2[c][j] = dz[c] * h[j]
-      }
+  for (int b0 = 0; b0 < B; b0 += kCaParamChunk) {
+    const int nb = min(kCaParamChunk, B - b0);
+    __syncthreads();
+    for (int i = tid; i < nb * 256; i += kCaThreads) {
+      const int b = i >> 8, k = (i >> 6) & 3, c = i & 63;
+      const size_t img = (size_t)layer * B + b0 + b;
+      sm[b][k][c] = k < 3 ? scratch[img * (64 + 2 * kCaMaxHidden) + k * 64 + c] : batch.mean[img * 64 + c];
     }
-    if (tid < hid) ab1 += __ldg(dh + tid);
-    if (tid < 64) ab2 += __ldg(dz + tid);
+    __syncthreads();
+    for (int b = 0; b < nb; ++b) {
+      const float* dz = sm[b][0];
+      const float* h = sm[b][1];
+      const float* dh = sm[b][2];
+      const float* m = sm[b][3];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int e = tid + i * kCaThreads;
+        if (e < n12) {
+          a1[i] = fmaf(dh[e / 64], m[e % 64], a1[i]);    // dw1[j][c] = dh[j] * m[c]
+          a2[i] = fmaf(dz[e / hid], h[e % hid], a2[i]);  // dw2[c][j] = dz[c] * h[j]
+        }
+      }
+      if (tid < hid) ab1 += dh[tid];
+      if (tid < 64) ab2 += dz[tid];
+    }
   }
 #pragma unroll
   for (int i = 0; i < 16; ++i) {

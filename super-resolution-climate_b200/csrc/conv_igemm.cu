@@ -793,7 +793,7 @@ static int launch_conv(const sres_conv_args* a, cudaStream_t stream) {
 
   int sms = device_sm_count();
   if (sms <= 0) return set_error(SRES_ERR_NO_DEVICE, "conv: no CUDA device");
-  int grid = p.n_tiles < sms ? p.n_tiles : sms;
+  int grid = persistent_grid(p.n_tiles, sms);
   cudaError_t e = cudaSuccess;
   int dev = 0;
   cudaGetDevice(&dev);

@@ -672,7 +672,7 @@ int launch_conv_n192(const sres_conv_args* a, cudaStream_t stream) {
 
   const int sms = device_sm_count();
   if (sms <= 0) return set_error(SRES_ERR_NO_DEVICE, "conv: no CUDA device");
-  const int grid = p.n_tiles < sms ? p.n_tiles : sms;
+  const int grid = persistent_grid(p.n_tiles, sms);
   int dev = 0;
   cudaGetDevice(&dev);
   int fl = (p.use_o16 ? kNO16 : 0) | (p.use_o32 ? kNO32 : 0) | (p.use_r32 ? kNR32 : 0) | (p.use_msk ? kNMsk : 0) |
@@ -736,7 +736,7 @@ int launch_conv_n48(const sres_conv_args* a, cudaStream_t stream) {
   if (rc) return rc;
   const int sms = device_sm_count();
   if (sms <= 0) return set_error(SRES_ERR_NO_DEVICE, "conv: no CUDA device");
-  const int grid = p.n_tiles < sms ? p.n_tiles : sms;
+  const int grid = persistent_grid(p.n_tiles, sms);
   int dev = 0;
   cudaGetDevice(&dev);
   static thread_local int attr_dev = -1;

@@ -13,6 +13,8 @@ int set_cuda_error(cudaError_t e, const char* where);
 
 // cached SM count of the current device (<=0 when there is none)
 int device_sm_count();
+// fewest CTAs of a persistent kernel that still finish n_tiles equal tiles in the minimal number of waves
+int persistent_grid(int n_tiles, int sms);
 
 // 2-D TMA descriptor over a row-major [nrows][64] bf16 matrix (128-byte rows), box = 64 x box_rows,
 // 128B swizzle, zero fill outside [0, nrows).

@@ -52,9 +52,8 @@ struct ProfRec { const char* cat; cudaEvent_t a, b; };
 static std::vector<ProfRec>* t_prof = nullptr;  // process-wide (autograd runs backward on its own thread)
 static std::mutex g_prof_mu;
 static bool prof_on() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("SRES_PROFILE"); v = (e && atoi(e) > 0) ? 1 : 0; }
-  return v == 1;
+  static const bool v = [] { const char* e = getenv("SRES_PROFILE"); return e && atoi(e) > 0; }();
+  return v;
 }
 struct ProfScope {
   cudaStream_t st; ProfRec r; bool on;
@@ -189,7 +188,7 @@ static int build_net(Net* n, const sres_rcan_desc* d, int training) {
   if (training) {
     n->o_ga = take(f32);
     n->o_gb16 = take(bf);
-    for (int k = 0; k < kRing; ++k) { n->o_dt2[k] = take(bf); n->o_dt1[k] = take(bf); }
+    for (int k = 0; k < ring_len(); ++k) { n->o_dt2[k] = take(bf); n->o_dt1[k] = take(bf); }
     if (!edsr) {
       n->o_ds = take((size_t)n->n_t * d->B * 64 * 4);
       n->o_gb32 = take(f32);
@@ -203,7 +202,8 @@ static int build_net(Net* n, const sres_rcan_desc* d, int training) {
       // gradient w.r.t. U[i] (level i+1), stored as f*f sub-grids of level-i rows (PixelUnshuffle layout)
       const int f2 = d->up_factor[i] * d->up_factor[i];
       n->o_du16[i] = take((size_t)f2 * n->lvRows[i] * 128);
-      n->o_du32[i] = take((size_t)f2 * n->lvRows[i] * 256);
+      // the fp32 accumulator of stage i's OUTPUT gradient is only written by stage i+1's input-gradient convs
+      if (i < d->n_up - 1) n->o_du32[i] = take((size_t)f2 * n->lvRows[i] * 256);
     }
     n->o_dres32 = take(f32);
     n->o_dres16 = take(bf);

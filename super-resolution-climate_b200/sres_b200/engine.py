@@ -151,10 +151,25 @@ class RcanEngine:
         d.res_scale = self.res_scale
         return d
 
+    MAX_SHAPES = 4   # workspaces (and their CUDA graphs) kept per engine; the least recently used shape is dropped
+
+    def _evict_shapes(self, keep):
+        """Ragged last batches and new inference shapes each need a multi-GB workspace: keep the MAX_SHAPES most recent."""
+        while len(self._ws) >= self.MAX_SHAPES:
+            old = next(k for k in self._ws if k != keep)
+            torch.cuda.synchronize(self.device)
+            for gk in [g for g in self._graphs if (g[1] == old if isinstance(g, tuple) and len(g) > 1 else False)]:
+                del self._graphs[gk]
+            del self._ws[old]
+            self._packed_version.pop(old, None)
+
     def workspace(self, B: int, H: int, W: int, training: bool) -> torch.Tensor:
         key = (B, H, W, training)
         ws = self._ws.get(key)
+        if ws is not None:
+            self._ws[key] = self._ws.pop(key)   # most recently used last
         if ws is None:
+            self._evict_shapes(key)
             nbytes = C.c_size_t(0)
             L.check(self.lib.sres_rcan_workspace_bytes(C.byref(self.desc(B, H, W)), int(training), C.byref(nbytes)),
                     "sres_rcan_workspace_bytes")
@@ -296,19 +311,31 @@ class RcanEngine:
                 # one graph per segment range; all ranges of a shape share the static dout / input buffers
                 dk = ("dout", key)
                 if dk not in self._graphs:
-                    self._graphs[dk] = dict(dout=dout.clone())
-                douts = self._graphs[dk]["dout"]
-                if seg_begin == 0:
+                    self._graphs[dk] = dict(dout=torch.empty_like(dout), token=None)
+                slot = self._graphs[dk]
+                douts = slot["dout"]
+                # refresh the static copy whenever the caller's output gradient is a different tensor or has been modified
+                # since the last copy (segments of one backward pass share it; a new pass always brings a new token)
+                token = (dout.data_ptr(), dout._version, self._fwd_generation.get(key, 0))
+                if slot["token"] != token:
                     douts.copy_(dout)
+                    slot["token"] = token
                 gk = ("bwd", key, bool(accumulate), seg_begin, seg_end)
                 g = self._graphs.get(gk)
                 if g is None:
+                    # first call of this segment range runs eagerly (lazy module loading and kernel attributes stay outside
+                    # capture, like forward); the second call captures
+                    self._launch_backward(key, fg["x"], douts, accumulate, seg_begin, seg_end)
+                    self._graphs[gk] = dict(graph=None)
+                elif g["graph"] is None:
                     graph = torch.cuda.CUDAGraph()
                     torch.cuda.synchronize(self.device)
                     with torch.cuda.graph(graph):
                         self._launch_backward(key, fg["x"], douts, accumulate, seg_begin, seg_end)
-                    g = self._graphs[gk] = dict(graph=graph)
-                g["graph"].replay()
+                    g["graph"] = graph
+                    graph.replay()
+                else:
+                    g["graph"].replay()
             else:
                 self._launch_backward(key, x, dout, accumulate, seg_begin, seg_end)
         if whole:
