@@ -115,6 +115,16 @@ SRES_API int sres_conv_mtiles(int B, int H, int W);
 SRES_API int sres_conv_supported(int H, int W, int n_out);
 SRES_API int sres_conv3x3_igemm(const sres_conv_args* args, void* stream);
 
+/* Two dependent identity-mapped 64 -> 64 convolutions in ONE persistent launch: the second reads the first's bf16 output
+ * (a2->in_bf16 == a1->out_bf16), tile by tile behind per-tile ready counters, so one pipeline fill / drain and the wave
+ * quantisation are paid once per pair.  Supported pairs (sres_conv_pair_supported): RCAB forward conv1 (bias, ReLU) ->
+ * conv2 (bias, SRES_EPI_POOL), network.py:55-59; RCAB backward dgrad(conv2) (ReLU mask) -> dgrad(conv1) (fp32
+ * read-modify-write, SRES_EPI_DOT).  flags: sres_conv_pair_flag_bytes() bytes of device memory, zero-filled ONCE (the
+ * counters reset themselves); do not share one flag buffer between launches that may overlap.                          */
+SRES_API size_t sres_conv_pair_flag_bytes(int B, int H, int W);
+SRES_API int sres_conv_pair_supported(const sres_conv_args* first, const sres_conv_args* second);
+SRES_API int sres_conv3x3_pair(const sres_conv_args* first, const sres_conv_args* second, void* flags, void* stream);
+
 /* Repack fp32 OIHW 3x3 weights (the checkpoint layout, state_dict of nn.Conv2d) to the bf16
  * tap-major operand the tensor-core kernels read.
  *   mode 0 (forward):   out[t][n][k] = w[oc(n)][k][ky][kx],              t = ky*3+kx

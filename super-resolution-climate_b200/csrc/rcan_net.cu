@@ -76,6 +76,12 @@ struct ProfScope {
 };
 #define PROF(cat) ProfScope prof_scope__(cat, st)
 
+#define RC0(x)           \
+  do {                   \
+    int rc__ = (x);      \
+    if (rc__) return rc__; \
+  } while (0)
+
 struct Net {
   sres_rcan_desc d;
   bool edsr;    // EDSR: one "group" of ResBlocks without channel attention, group-tail conv or group skip
@@ -93,6 +99,7 @@ struct Net {
   size_t o_xb, o_t1, o_t2, o_mean, o_s, o_ds, o_resb, o_u[4];
   size_t o_hf, o_gf[2], o_xf, o_pool_part, o_pool_sum;
   size_t o_sbias;  // EDSR: res_scale * bias of every ResBlock's second conv
+  size_t o_pair_flags;   // ready / consumed counters of the fused convolution pairs, two sets (alternating RCABs)
   size_t o_ga, o_gb32, o_gb16, o_dt2[kRing], o_dt1[kRing], o_ds_part, o_wg_ws, o_sw_ws, o_ca_scr, o_du16[4], o_du32[4], o_dres32, o_dres16;
   size_t total;
   int n_xb, n_t;  // saved-buffer counts (1 in inference mode)
@@ -185,6 +192,7 @@ static int build_net(Net* n, const sres_rcan_desc* d, int training) {
   n->o_xf = take(f32);
   n->o_pool_part = take((size_t)sres_conv_mtiles(d->B, d->H, d->W) * 2 * 4 * 64 * 4);
   n->o_pool_sum = take((size_t)d->B * 64 * 4);
+  n->o_pair_flags = take(2 * sres_conv_pair_flag_bytes(d->B, d->H, d->W));
   if (training) {
     n->o_ga = take(f32);
     n->o_gb16 = take(bf);
@@ -287,19 +295,38 @@ static int pack_all(const Net& n, const float* params, uint8_t* ws, cudaStream_t
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-static int conv64(const void* in, const void* wp, const float* bias, int B, int H, int W, void* st, float* out_f32,
-                  void* out_bf16, unsigned flags = 0, float* pool = nullptr, const float* resid = nullptr,
-                  const float* resid2 = nullptr, const void* mask = nullptr, int map = SRES_MAP_IDENT, int si = 0,
-                  int sj = 0, int sf = 2) {
-  PROF(map != SRES_MAP_IDENT ? "conv shuffle/unshuffle" : (flags & SRES_EPI_DOT) ? "conv dgrad +fp32 rmw +ds-dot" : mask ? "conv dgrad+relu-mask" : (resid && out_f32) ? "conv +fp32 addend (rmw)"
-       : (flags & SRES_EPI_POOL) ? "conv fwd +pool" : (flags & SRES_EPI_RELU) ? "conv fwd +relu" : "conv other");
+static sres_conv_args conv64_args(const void* in, const void* wp, const float* bias, int B, int H, int W, float* out_f32,
+                                  void* out_bf16, unsigned flags = 0, float* pool = nullptr, const float* resid = nullptr,
+                                  const float* resid2 = nullptr, const void* mask = nullptr, int map = SRES_MAP_IDENT,
+                                  int si = 0, int sj = 0, int sf = 2) {
   sres_conv_args a;
   memset(&a, 0, sizeof(a));
   a.in_bf16 = in; a.wpack_bf16 = wp; a.bias = bias; a.resid_f32 = resid; a.resid2_f32 = resid2; a.mask_bf16 = mask;
   a.out_f32 = out_f32; a.out_bf16 = out_bf16; a.pool_part = pool;
   a.B = B; a.H = H; a.W = W; a.n_out = 64; a.epi_flags = flags; a.map_mode = map; a.sub_i = si; a.sub_j = sj;
   a.shuffle_factor = sf;
+  return a;
+}
+
+static int conv64(const void* in, const void* wp, const float* bias, int B, int H, int W, void* st, float* out_f32,
+                  void* out_bf16, unsigned flags = 0, float* pool = nullptr, const float* resid = nullptr,
+                  const float* resid2 = nullptr, const void* mask = nullptr, int map = SRES_MAP_IDENT, int si = 0,
+                  int sj = 0, int sf = 2) {
+  PROF(map != SRES_MAP_IDENT ? "conv shuffle/unshuffle" : (flags & SRES_EPI_DOT) ? "conv dgrad +fp32 rmw +ds-dot" : mask ? "conv dgrad+relu-mask" : (resid && out_f32) ? "conv +fp32 addend (rmw)"
+       : (flags & SRES_EPI_POOL) ? "conv fwd +pool" : (flags & SRES_EPI_RELU) ? "conv fwd +relu" : "conv other");
+  const sres_conv_args a = conv64_args(in, wp, bias, B, H, W, out_f32, out_bf16, flags, pool, resid, resid2, mask, map, si, sj, sf);
   return sres_conv3x3_igemm(&a, st);
+}
+
+// two dependent convolutions: one fused launch when the pair kernel takes them, else one after the other
+static int conv64_pair(const sres_conv_args& a1, const sres_conv_args& a2, void* flags, void* st, const char* cat) {
+  if (sres_conv_pair_supported(&a1, &a2)) {
+    PROF(cat);
+    return sres_conv3x3_pair(&a1, &a2, flags, st);
+  }
+  { PROF((a1.epi_flags & SRES_EPI_RELU) ? "conv fwd +relu" : "conv dgrad+relu-mask"); RC0(sres_conv3x3_igemm(&a1, st)); }
+  PROF((a2.epi_flags & SRES_EPI_DOT) ? "conv dgrad +fp32 rmw +ds-dot" : "conv fwd +pool");
+  return sres_conv3x3_igemm(&a2, st);
 }
 
 #define RC(x)            \
@@ -347,9 +374,10 @@ static int forward(const Net& n, const float* P, const float* x, float* out, uin
       const float* b1 = w1 + n.hid * 64;
       const float* w2 = b1 + n.hid;
       const float* b2 = w2 + 64 * n.hid;
-      RC(conv64(XB(xbi), WF(n.cidx(g, r, 0)), c1b, B, H, W, st, nullptr, T1(ti), SRES_EPI_RELU));
-      RC(conv64(T1(ti), WF(n.cidx(g, r, 1)), c2b, B, H, W, st, nullptr, T2(ti), fused_pool ? SRES_EPI_POOL : 0,
-                fused_pool ? pool_part : nullptr));
+      RC(conv64_pair(conv64_args(XB(xbi), WF(n.cidx(g, r, 0)), c1b, B, H, W, nullptr, T1(ti), SRES_EPI_RELU),
+                     conv64_args(T1(ti), WF(n.cidx(g, r, 1)), c2b, B, H, W, nullptr, T2(ti), fused_pool ? SRES_EPI_POOL : 0,
+                                 fused_pool ? pool_part : nullptr),
+                     ws + n.o_pair_flags + (size_t)(ti & 1) * sres_conv_pair_flag_bytes(B, H, W), st, "conv pair fwd (conv1 -> conv2 +pool)"));
       if (!fused_pool) RC(sres_ca_pool(T2(ti), pool_sum, B, H, W, st));
       float* mean = (float*)(ws + n.o_mean) + (size_t)(training ? ti : 0) * B * 64;
       float* sv = (float*)(ws + n.o_s) + (size_t)(training ? ti : 0) * B * 64;
@@ -582,12 +610,17 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
         else RC(sres_ca_bwd(gb32, T2(ti), w1, b1, w2, b2, n.hid, mean, (float*)(ws + n.o_ds_part), dt2, dsv, B, H, W, st)); }
         RC(wq.push(T1(ti), dt2, B, H, W, gr + kConvW + 64, gr + 2 * kConvW + 64, 64, 1, 0, accumulate));
         RC(wq.before_write(dt1));
-        RC(conv64(dt2, WD(n.cidx(g, r, 1)), nullptr, B, H, W, st, nullptr, dt1, 0, nullptr, nullptr, nullptr, T1(ti)));
-        RC(wq.push(XB(xb0 + r), dt1, B, H, W, gr, gr + kConvW, 64, 1, 0, accumulate));
         if (r > 0) {
-          RC(conv64(dt1, WD(n.cidx(g, r, 0)), nullptr, B, H, W, st, gb32, nullptr, fused_dot ? SRES_EPI_DOT : 0,
-                    fused_dot ? dot_part : nullptr, gb32, nullptr, fused_dot ? T2(ti - 1) : nullptr));
+          // dgrad of conv2 (ReLU mask) and dgrad of conv1 (fp32 read-modify-write of the gradient trunk + sum g*t2) as one launch
+          RC(conv64_pair(conv64_args(dt2, WD(n.cidx(g, r, 1)), nullptr, B, H, W, nullptr, dt1, 0, nullptr, nullptr, nullptr, T1(ti)),
+                         conv64_args(dt1, WD(n.cidx(g, r, 0)), nullptr, B, H, W, gb32, nullptr, fused_dot ? SRES_EPI_DOT : 0,
+                                     fused_dot ? dot_part : nullptr, gb32, nullptr, fused_dot ? T2(ti - 1) : nullptr),
+                         ws + n.o_pair_flags + (size_t)(ti & 1) * sres_conv_pair_flag_bytes(B, H, W), st,
+                         "conv pair bwd (dgrad2 -> dgrad1 +rmw +dot)"));
+          RC(wq.push(XB(xb0 + r), dt1, B, H, W, gr, gr + kConvW, 64, 1, 0, accumulate));
         } else {
+          RC(conv64(dt2, WD(n.cidx(g, r, 1)), nullptr, B, H, W, st, nullptr, dt1, 0, nullptr, nullptr, nullptr, T1(ti)));
+          RC(wq.push(XB(xb0 + r), dt1, B, H, W, gr, gr + kConvW, 64, 1, 0, accumulate));
           // grad wrt the group input = body path (gb32 + conv1 dgrad) + group skip (ga)
           RC(wq.before_write(gb16));
           RC(conv64(dt1, WD(n.cidx(g, r, 0)), nullptr, B, H, W, st, ga, gb16, 0, nullptr, gb32, ga));

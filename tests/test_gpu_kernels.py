@@ -135,6 +135,63 @@ def test_conv_n192_matches_tap_per_mma_kernel(env, B, H, W):
         assert torch.equal(results[0][1].nan_to_num(0.0), results[1][1].nan_to_num(0.0)), name
 
 
+@pytest.mark.parametrize("B,H,W", [(3, 20, 24), (5, 48, 48), (64, 48, 48), (2, 96, 96)])
+def test_conv_pair_equals_two_launches(env, B, H, W):
+    """The fused two-convolution launch (phase 2 reads phase 1's tiles behind per-tile ready counters) computes exactly what
+    the two separate launches compute -- same MMAs, same epilogue arithmetic: every output bit-equal, per-tile partial
+    sums bit-equal -- for the RCAB forward pair (conv1 -> conv2 + pool) and the backward pair (dgrad2 -> dgrad1 with the
+    fp32 read-modify-write and the sum g*t2).  Repeated launches on one flag buffer check that the counters clean
+    themselves (all zero afterwards) and that nothing depends on timing."""
+    L, lib, dev = env
+    lib.sres_conv_pair_flag_bytes.restype = C.c_size_t
+    rows = lib.sres_ptl_rows(B, H, W)
+    nt = (rows + 127) // 128
+    flags = torch.zeros(lib.sres_conv_pair_flag_bytes(B, H, W) // 4, dtype=torch.int32, device=dev)
+    xin = to_ptl(bf16_round(torch.randn(B, 64, H, W)).to(dev), torch.bfloat16)
+    t1m = to_ptl(torch.randn(B, 64, H, W).to(dev), torch.bfloat16)
+    t2f = to_ptl(torch.randn(B, 64, H, W).to(dev), torch.bfloat16)
+    trunk = to_ptl(torch.randn(B, 64, H, W).to(dev), torch.float32)
+    w1 = pack(lib, (torch.randn(64, 64, 3, 3) * 0.05).to(dev), 0)
+    w2 = pack(lib, (torch.randn(64, 64, 3, 3) * 0.05).to(dev), 1)
+    b1, b2 = torch.randn(64, device=dev), torch.randn(64, device=dev)
+
+    def bufs():
+        return dict(mid=torch.full((rows, 64), float("nan"), device=dev, dtype=torch.bfloat16),
+                    o16=torch.full((rows, 64), float("nan"), device=dev, dtype=torch.bfloat16),
+                    o32=trunk.clone(), part=torch.full((nt, 2, 4, 64), float("nan"), device=dev))
+
+    def fwd_args(bf):
+        a1 = conv_args(in_bf16=xin, wpack_bf16=w1, bias=b1, out_bf16=bf["mid"], B=B, H=H, W=W, n_out=64, epi_flags=L.EPI_RELU)
+        a2 = conv_args(in_bf16=bf["mid"], wpack_bf16=w2, bias=b2, out_bf16=bf["o16"], pool_part=bf["part"], B=B, H=H, W=W, n_out=64,
+                       epi_flags=L.EPI_POOL)
+        return a1, a2
+
+    def bwd_args(bf):
+        a1 = conv_args(in_bf16=xin, wpack_bf16=w1, mask_bf16=t1m, out_bf16=bf["mid"], B=B, H=H, W=W, n_out=64)
+        a2 = conv_args(in_bf16=bf["mid"], wpack_bf16=w2, mask_bf16=t2f, out_f32=bf["o32"], resid_f32=bf["o32"], pool_part=bf["part"],
+                       B=B, H=H, W=W, n_out=64, epi_flags=L.EPI_DOT)
+        return a1, a2
+
+    for name, mk in (("forward pair", fwd_args), ("backward pair", bwd_args)):
+        ref = bufs()
+        a1, a2 = mk(ref)
+        a1.debug_flags = a2.debug_flags = 64          # two launches of the tap-per-MMA kernel
+        run_conv(lib, a1)
+        run_conv(lib, a2)
+        for rep in range(6):
+            got = bufs()
+            a1, a2 = mk(got)
+            if not lib.sres_conv_pair_supported(C.byref(a1), C.byref(a2)):
+                assert W > 62 and name == "backward pair"     # wide halo ring + 64 KB of epilogue slabs do not fit: two launches
+                break
+            L.check(lib.sres_conv3x3_pair(C.byref(a1), C.byref(a2), ptr(flags), L.cur_stream()), "sres_conv3x3_pair")
+            torch.cuda.synchronize()
+            assert int(flags.abs().sum()) == 0, (name, rep, "ready / consumed counters must reset themselves")
+            for k in ("mid", "o16", "o32", "part"):
+                a, b = got[k], ref[k]
+                assert torch.equal(a.float().nan_to_num(7.0), b.float().nan_to_num(7.0)), (name, rep, k)
+
+
 @pytest.mark.parametrize("B,H,W", [(3, 20, 24), (5, 48, 48)])
 def test_conv_epilogue_flavours_agree(env, B, H, W):
     """The tap-per-MMA kernel (debug flag 64; wide-image / PixelShuffle paths and the A/B baseline of the N = 192 kernel):
