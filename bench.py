@@ -393,37 +393,55 @@ def run_cuda(args):
     infer_tiles_s = world * B * args.steps / (float(t.item()) / 1e3)
     model.train()
 
-    # ---- roofline of the dominant kernel: the 64->64 tensor-core conv, timed live with CUDA events ---
+    # ---- roofline of the dominant kernel, timed live with CUDA events on the launching stream -----------------------
+    # The RCAB loop runs its two convolutions as ONE fused launch (conv1 + ReLU -> conv2 + pool partials,
+    # sres_conv3x3_pair): 2 x 10.87 GFLOP per launch.  With SRES_CONV_FUSE=0 the single conv1 launch is measured instead.
     import ctypes as C
     rows = B * (TILE + 1) * (TILE + 1)
     nact = 24  # rotate over 24 activation buffers (24 x 19.7 MB >> L2) so the operand is not L2-resident
     acts = [torch.randn(rows, 64, device=dev).bfloat16() for _ in range(nact)]
+    midb = torch.empty(rows, 64, device=dev, dtype=torch.bfloat16)
     outb = torch.empty(rows, 64, device=dev, dtype=torch.bfloat16)
     wpack = torch.randn(9 * 64 * 64, device=dev).bfloat16()
     bias = torch.zeros(64, device=dev)
-    ca = L.ConvArgs()
-    ca.wpack_bf16, ca.bias, ca.out_bf16 = wpack.data_ptr(), bias.data_ptr(), outb.data_ptr()
-    ca.B, ca.H, ca.W, ca.n_out, ca.epi_flags = B, TILE, TILE, 64, L.EPI_RELU
     lib = L.lib()
+    lib.sres_conv_pair_flag_bytes.restype = C.c_size_t
+    partb = torch.zeros(lib.sres_conv_mtiles(B, TILE, TILE), 2, 4, 64, device=dev)
+    flagb = torch.zeros(lib.sres_conv_pair_flag_bytes(B, TILE, TILE) // 4, dtype=torch.int32, device=dev)
+    ca = L.ConvArgs()
+    ca.wpack_bf16, ca.bias, ca.out_bf16 = wpack.data_ptr(), bias.data_ptr(), midb.data_ptr()
+    ca.B, ca.H, ca.W, ca.n_out, ca.epi_flags = B, TILE, TILE, 64, L.EPI_RELU
+    cb = L.ConvArgs()
+    cb.in_bf16, cb.wpack_bf16, cb.bias, cb.out_bf16, cb.pool_part = midb.data_ptr(), wpack.data_ptr(), bias.data_ptr(), outb.data_ptr(), partb.data_ptr()
+    cb.B, cb.H, cb.W, cb.n_out, cb.epi_flags = B, TILE, TILE, 64, L.EPI_POOL
     st = L.cur_stream()
+    ca.in_bf16 = acts[0].data_ptr()
+    fused = bool(lib.sres_conv_pair_supported(C.byref(ca), C.byref(cb)))
+
+    def launch(i):
+        ca.in_bf16 = acts[i % nact].data_ptr()
+        if fused:
+            return lib.sres_conv3x3_pair(C.byref(ca), C.byref(cb), C.c_void_p(flagb.data_ptr()), st)
+        return lib.sres_conv3x3_igemm(C.byref(ca), st)
+
     reps = 48
     for i in range(8):
-        ca.in_bf16 = acts[i % nact].data_ptr()
-        L.check(lib.sres_conv3x3_igemm(C.byref(ca), st), "conv")
+        L.check(launch(i), "conv")
     e0.record()
     for i in range(reps):
-        ca.in_bf16 = acts[i % nact].data_ptr()
-        lib.sres_conv3x3_igemm(C.byref(ca), st)
+        launch(i)
     e1.record()
     torch.cuda.synchronize()
     conv_ms = e0.elapsed_time(e1) / reps
-    conv_flops = 2.0 * B * TILE * TILE * 64 * 64 * 9
+    conv_flops = 2.0 * B * TILE * TILE * 64 * 64 * 9 * (2 if fused else 1)
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+    kernel_name = ("conv3x3_pair_kernel<17,33> (fused RCAB forward pair: 64->64 conv + bias + ReLU -> 64->64 conv + bias + CA pool partials, bf16 out, B=64, 48x48)"
+                   if fused else "conv3x3_igemm_kernel<64,false,17> (64->64 conv + bias + ReLU, bf16 out: RCAB conv1, B=64, 48x48)")
 
     # ---- BASELINE configs 4 and 5 (all ranks take part) ------------------------------------------------
     region = x8 = None
     if not args.skip_extras:
-        del acts, outb
+        del acts, outb, midb
         torch.cuda.empty_cache()
         region = bench_region(trainer, dev, world, rank)
         x8 = bench_x8(dev, world, rank, max(3, min(args.steps, 10)))
@@ -439,10 +457,12 @@ def run_cuda(args):
         cpu = cpu_baseline_subprocess()
 
     # DRAM traffic of the dominant kernel: NOT measured in this run -- read from the committed `ncu --set full` capture of
-    # the same kernel and shape (profiles/r01_v4_conv_ncu_metrics.json; the kernel's data path has not changed since)
+    # the same kernel and shape (profiles/r02_pair_ncu_metrics.json for the fused pair, profiles/r01_v4_conv_ncu_metrics.json
+    # for the single convolution)
     traffic = None
+    cap = "r02_pair_ncu_metrics.json" if fused else "r01_v4_conv_ncu_metrics.json"
     try:
-        m = json.load(open(os.path.join(ROOT, "profiles", "r01_v4_conv_ncu_metrics.json")))
+        m = json.load(open(os.path.join(ROOT, "profiles", cap)))
         conv = {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Gbyte": 1e9}
         traffic = sum(float(m[k]["value"].replace(",", "")) * conv[m[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
     except Exception:
@@ -459,10 +479,11 @@ def run_cuda(args):
         "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": B * CH * S * S * 4, "d2h_bytes_per_step": 4},
         "gpu_launches": per_step_launches * args.steps,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv3x3_igemm_kernel<64,false,17> (64->64 conv + bias + ReLU, bf16 out: RCAB conv1, B=64, 48x48)", "achieved": achieved,
+        "roofline": {"bound": "tensor", "kernel": kernel_name, "achieved": achieved, "flops_per_launch": conv_flops,
                      "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_burst"], "traffic": traffic,
-                     "traffic_note": "from committed capture r01 (ncu --set full, profiles/r01_v4_conv_ncu_metrics.json), not measured in this run: DRAM bytes per launch; algorithmic 39.3 MB "
-                                     "(19.7 in + 19.7 out): the input is read once, the output is still in L2 when the kernel ends",
+                     "traffic_note": f"from committed capture (ncu --set full, profiles/{cap}), not measured in this run: DRAM bytes per launch; "
+                                     + ("algorithmic 59 MB (19.7 in + 19.7 intermediate + 19.7 out): the intermediate and the output are still in L2 when the kernel ends"
+                                        if fused else "algorithmic 39.3 MB (19.7 in + 19.7 out): the input is read once, the output is still in L2 when the kernel ends"),
                      "peak_source": pk["src"] + " burst (kernel timed alone)", "us_per_launch": conv_ms * 1e3,
                      "step_tflops_per_gpu": step_tflops, "step_frac_of_sustained": step_tflops / pk["tflops_sustained"]},
         "cpu_baseline": cpu,
