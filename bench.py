@@ -190,7 +190,8 @@ def bench_region(trainer, dev, world, rank, reps=3):
     """Config 4 end to end through ModelTrainer.process_image: the (2, 3000, 17280) fp32 region starts in pinned HOST
     memory; tile extraction + NaN-tile drop, lnorm, bicubic down, RCAN-full forward (no grad), de-normalise + stitch, and the
     copy of the stitched images (input / target / interpolated / model of both variables) back to host memory are all
-    inside the timed region.  Under torchrun the tile batches are sharded over the ranks and gathered."""
+    inside the timed region.  Under torchrun rank 0 copies the region to its GPU and broadcasts it, the tile batches are
+    sharded over the ranks, the products are gathered and rank 0 stitches and copies the images out."""
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -217,10 +218,13 @@ def bench_region(trainer, dev, world, rank, reps=3):
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             if rep > 0:
                 times.append(float(dt.item()))
-            img = images[list(images)[0]]["model"]
-            ntiles = int(np.isfinite(img[::TILE * SCALE, ::TILE * SCALE]).sum())
-            bytes_out = sum(a.nbytes for v in images.values() for a in v.values())
-            del images, img
+            ntiles = int(trainer.get_dataset().timeslice.shape[0])     # tiles that survived the NaN-tile drop
+            if rank == 0:   # (under torchrun the images are stitched and copied to the host on rank 0 only)
+                img = images[list(images)[0]]["model"]
+                assert int(np.isfinite(img[::TILE * SCALE, ::TILE * SCALE]).sum()) == ntiles
+                bytes_out = sum(a.nbytes for v in images.values() for a in v.values())
+                del img
+            del images
     finally:
         cfg().task["tile_order"] = saved_order
         trainer.model_manager._dataset = saved_ds

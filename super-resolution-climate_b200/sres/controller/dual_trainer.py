@@ -300,8 +300,13 @@ class ModelTrainer(object):
         mean_model = float(lsum[0] / lsum[2]) if float(lsum[2]) > 0 else float("nan")
         mean_interp = float(lsum[1] / lsum[2]) if float(lsum[2]) > 0 else float("nan")
         images, losses = {}, {}
+        # data parallel: the stitched images are built (and copied to the host) on rank 0 only -- eight ranks each pulling
+        # 2.4 GB of float64 images through the same host memory made the 8-GPU pass slower than one GPU (all_ranks=True
+        # restores the replicated result)
+        stitch_here = self.world == 1 or self.rank == 0 or kwargs.get("all_ranks", False)
         for ivar, vname in enumerate(output_vars):
-            images[vname] = self.assemble_images(batches, ivar, timeslice.coords["tiles"], timeslice.attrs["grid_shape"], stats)
+            if stitch_here:
+                images[vname] = self.assemble_images(batches, ivar, timeslice.coords["tiles"], timeslice.attrs["grid_shape"], stats)
             losses[vname] = dict(model=mean_model, interpolated=mean_interp)
         return images, losses
 

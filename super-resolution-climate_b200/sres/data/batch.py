@@ -155,12 +155,33 @@ class BatchDataset(object):
 
     def load_timeslice(self, time_index: int, **kwargs) -> TileArray:
         if time_index != self.time_index:
-            region = self.load_region_data(time_index)
-            region = (region if isinstance(region, torch.Tensor) else torch.from_numpy(region)).to(get_device(), non_blocking=True)
-            region = region.contiguous().float()
+            region = self._load_region_on_device(time_index)
             self.timeslice = self.get_tiles(region)
             self.time_index = time_index
         return self.timeslice
+
+    def _load_region_on_device(self, time_index: int) -> torch.Tensor:
+        """The (C,Y,X) region of a time index on this rank's GPU.  Under torch.distributed every rank needs the same region
+        (tile ids are global): rank 0 reads / generates it, copies it to its GPU once and broadcasts it over NVLink, instead
+        of every rank pulling the same hundreds of megabytes through host memory."""
+        import torch.distributed as dist
+        dev = get_device()
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        if world == 1 or dev.type != "cuda":
+            region = self.load_region_data(time_index)
+            region = (region if isinstance(region, torch.Tensor) else torch.from_numpy(region)).to(dev, non_blocking=True)
+            return region.contiguous().float()
+        if dist.get_rank() == 0:
+            region = self.load_region_data(time_index)
+            region = (region if isinstance(region, torch.Tensor) else torch.from_numpy(region)).to(dev, non_blocking=True).contiguous().float()
+            shape = torch.tensor(list(region.shape), dtype=torch.int64, device=dev)
+        else:
+            region, shape = None, torch.zeros(3, dtype=torch.int64, device=dev)
+        dist.broadcast(shape, src=0)
+        if region is None:
+            region = torch.empty(tuple(int(v) for v in shape.tolist()), dtype=torch.float32, device=dev)
+        dist.broadcast(region, src=0)
+        return region
 
     # -- batches ---------------------------------------------------------------------------------
     def select_batch(self, tile_range) -> Optional[TileArray]:

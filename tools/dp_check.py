@@ -36,6 +36,26 @@ same = torch.tensor([float((gd - gr).abs().max())], device=dev)
 allg = [torch.zeros_like(gd) for _ in range(world)]
 dist.all_gather(allg, gd)
 ident = all(torch.equal(allg[0], a) for a in allg)
+# ---- ragged global step: ranks hold batches of DIFFERENT sizes and the last rank only rides along (weight 0): the reduced
+# gradient must equal the single-GPU gradient of the union of the live batches (global RMSE = sqrt(sum SSE / sum N))
+sizes = [B if r % 2 == 0 else B - 1 for r in range(world)]
+live = [r < world - 1 or world == 1 for r in range(world)]
+offs = [sum(sizes[:r]) for r in range(world)]
+hr_r = hr_all[offs[rank]:offs[rank] + sizes[rank]].contiguous()
+for p in model.parameters(): p.grad = None
+prd = model(snn.bicubic_resize(hr_r, 0.25).requires_grad_(True))
+loss_g = snn.loss(prd, hr_r, "l2", dist.group.WORLD, 1.0 if live[rank] else 0.0)
+loss_g.backward()
+torch.cuda.synchronize()
+union = torch.cat([hr_all[offs[r]:offs[r] + sizes[r]] for r in range(world) if live[r]]).contiguous()
+for p in ref.parameters(): p.grad = None
+loss_u = snn.loss(ref(snn.bicubic_resize(union, 0.25).requires_grad_(True)), union, "l2")
+loss_u.backward()
+torch.cuda.synchronize()
+rel_ragged = ((model.engine.flat_grad - ref.engine.flat_grad).norm() / ref.engine.flat_grad.norm()).item()
+ragged_ok = rel_ragged < 1e-4 and abs(loss_g.item() - loss_u.item()) < 1e-5 * abs(loss_u.item())
+if rank == 0:
+    print(f"RESULT ragged DP-{world}: sizes {sizes}, live {live}: gradient rel {rel_ragged:.3e}, loss {loss_g.item():.6f} vs {loss_u.item():.6f} -> {'OK' if ragged_ok else 'FAIL'}")
 # ---- sharded inference through the mirrored trainer: DP-N stitched images == single-GPU stitched images ----------
 import numpy as np, tempfile
 from sres.base.util.config import ConfigContext
@@ -48,10 +68,10 @@ wc = WorkflowController("sres", dict(task="SSS_SST-tiles-48", dataset="synthetic
 wc.initialize("sres", "rcan-10-20-64", **over)
 tr = wc.trainer
 dist.broadcast(tr.model.engine.flat, src=0); tr.model.engine.mark_params_changed()
-images, losses = wc.inference(0, ResultStructure.Image)
+images, losses = wc.inference(0, ResultStructure.Image)       # stitched on rank 0 only
 tr.world, tr.rank = 1, 0           # the same trainer, unsharded
 images1, losses1 = tr.process_image(TSet.Validation, 0, interp_loss=True)
-same_img = all(np.array_equal(images[v][k], images1[v][k], equal_nan=True) for v in images for k in images[v])
+same_img = all(np.array_equal(images[v][k], images1[v][k], equal_nan=True) for v in images for k in images[v]) and (rank != 0 or len(images) == len(images1) > 0)
 same_loss = all(abs(losses[v]["model"] - losses1[v]["model"]) < 1e-6 for v in losses)
 # ---- data-parallel training through the trainer loop: same shuffles on every rank, replicas stay identical ----------
 tr.world, tr.rank = world, rank
