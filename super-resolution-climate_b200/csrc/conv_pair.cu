@@ -44,6 +44,7 @@ struct PairParams {
   unsigned* consumed;      // [n_tiles] phase-2 tiles that have seen ready[t]
   long long* timeline;     // bring-up only: per-CTA clock stamps [grid][16]
   int fence_mode;          // proxy fence around the global hand-over (see fence_proxy_async_mode)
+  int dual_w;              // 1: the phase-2 weights have their own 72 KB of shared memory and are loaded at kernel start
 };
 
 constexpr int kPO16 = 1, kPO32 = 2, kPR32 = 4, kPMsk = 8, kPRelu = 16, kPPool = 32, kPDot = 64;
@@ -234,7 +235,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_w = smem;
-  uint8_t* smem_a = smem + kPWBytes;
+  uint8_t* smem_w2 = smem + (p.dual_w ? kPWBytes : 0);
+  uint8_t* smem_a = smem + kPWBytes * (p.dual_w ? 2 : 1);
   const int stage_bytes = p.stage_rows * 128;
   uint8_t* tail = smem + p.off_tail;
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(tail);   // [kPStages]
@@ -297,6 +299,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
     if (leader) {
       mbar_expect_tx(&bar_w[0], kPWBytes);
       for (int t = 0; t < 9; ++t) tma_load_2d(smem_w + t * 64 * 128, &tmW1, &bar_w[0], 0, t * 64);
+      if (p.dual_w) {   // room for both weight sets: no swap between the phases
+        mbar_expect_tx(&bar_w[1], kPWBytes);
+        for (int t = 0; t < 9; ++t) tma_load_2d(smem_w2 + t * 64 * 128, &tmW2, &bar_w[1], 0, t * 64);
+      }
     }
     pdl_wait();
     int it = 0;
@@ -313,13 +319,15 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
       __syncwarp();
     }
     // phase-2 weights replace phase 1's once every phase-1 MMA of this CTA has retired (its last ring slot was released)
-    if (n1 > 0) mbar_wait(&bar_empty[(n1 - 1) % p.nstage], ((n1 - 1) / p.nstage) & 1, 7);
-    PSTAMP(2);   // every phase-1 MMA retired
-    if (leader) {
-      mbar_expect_tx(&bar_w[1], kPWBytes);
-      for (int t = 0; t < 9; ++t) tma_load_2d(smem_w + t * 64 * 128, &tmW2, &bar_w[1], 0, t * 64);
+    if (!p.dual_w) {
+      if (n1 > 0) mbar_wait(&bar_empty[(n1 - 1) % p.nstage], ((n1 - 1) / p.nstage) & 1, 7);
+      PSTAMP(2);   // every phase-1 MMA retired
+      if (leader) {
+        mbar_expect_tx(&bar_w[1], kPWBytes);
+        for (int t = 0; t < 9; ++t) tma_load_2d(smem_w + t * 64 * 128, &tmW2, &bar_w[1], 0, t * 64);
+      }
+      __syncwarp();
     }
-    __syncwarp();
     // Lanes 0..2 watch one phase-1 tile each (t-1, t, t+1 cover this tile's halo window: P + 1 <= 128 rows).  The counters
     // clean themselves -- the last of the (up to three) phase-2 tiles that has seen ready[t] resets it -- and that
     // bookkeeping runs one tile behind, its atomic in flight while the lane spins on the next counter, so the producer stays
@@ -372,7 +380,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
     const bool leader = elect_one();
     constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
     constexpr uint32_t dhi = sdesc_hi_sw128(1024);
-    const uint32_t w_lo = sdesc_lo(smem_u32(smem_w), 16);
+    uint32_t w_lo = sdesc_lo(smem_u32(smem_w), 16);
     const uint32_t a_lo0 = sdesc_lo(smem_u32(smem_a), 16);
     const uint32_t row_step = uint32_t(p.P) * 8;
     int it = 0;
@@ -380,6 +388,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
     for (int phase = 0; phase < 2; ++phase) {
       mbar_wait(&bar_w[phase], 0, 2);
       tc_fence_after();
+      if (phase == 1) w_lo = sdesc_lo(smem_u32(smem_w2), 16);
       PSTAMP(3 + 3 * phase);   // weights of this phase landed
       for (int tile = phase ? c2 : c1; tile < p.n_tiles; tile += G, ++it) {
         const int slot = it % p.nstage;
@@ -536,12 +545,18 @@ static bool pair_plan(int W, bool fwd, PairParams* p, size_t* smem_bytes) {
   const int rows = 128 + 2 * (W + 2);
   const int box = (rows + 7) / 8 * 8 <= 256 ? (rows + 7) / 8 * 8 : 64;   // the whole window as one TMA box when it fits
   const int stage_rows = (rows + box - 1) / box * box;
+  static const int dual_env = [] { const char* e = getenv("SRES_PAIR_DUALW"); return e ? atoi(e) : 1; }();
+  int dual = 0;
   int ns = (smem_max - 1024 - kPWBytes - 1024 - slab) / (stage_rows * 128);
+  if (dual_env) {   // both weight sets resident when that still leaves a ring of dual_env + 1 slots or more
+    const int ns2 = (smem_max - 1024 - 2 * kPWBytes - 1024 - slab) / (stage_rows * 128);
+    if (ns2 >= 2 && ns2 >= dual_env + 1) { dual = 1; ns = ns2; }
+  }
   if (ns > kPStages) ns = kPStages;
   if (ns < 2) return false;
   if (p) {
-    p->box_rows = box; p->stage_rows = stage_rows; p->nstage = ns;
-    int off = kPWBytes + ns * stage_rows * 128;
+    p->box_rows = box; p->stage_rows = stage_rows; p->nstage = ns; p->dual_w = dual;
+    int off = kPWBytes * (dual ? 2 : 1) + ns * stage_rows * 128;
     p->off_s16 = off; off += 16384;
     p->off_msk = off; off += fwd ? 0 : 16384;
     p->off_s32 = off; off += fwd ? 0 : 32768;
