@@ -147,7 +147,7 @@ SRES_API int sres_pack_conv_weights(const float* w_oihw, void* out_bf16, int mod
 SRES_API size_t sres_conv_wgrad_workspace_bytes(void);
 /* Several independent weight gradients of the same geometry in ONE launch (split-K CTAs are divided
  * between the jobs; fewer partials per job, one prologue / accumulator drain per batch).            */
-#define SRES_WGRAD_MAX_JOBS 8
+#define SRES_WGRAD_MAX_JOBS 16
 typedef struct sres_wgrad_job {
   const void* x_bf16;      /* conv input, bf16 PTL                                               */
   const void* dy_bf16;     /* gradient of the conv output, bf16 PTL                              */

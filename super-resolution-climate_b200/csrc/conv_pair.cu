@@ -5,15 +5,18 @@
 // and every launch pays its own pipeline fill (barriers, TMEM, 72 KB of weights, the first halo window, the first tile's
 // MMAs with nothing to overlap) and drain (the last tile's epilogue) -- together about a third of the kernel.  The second
 // convolution of a pair needs, for its tile t, only tiles t-1, t, t+1 of the first (the halo is P+1 <= 128 rows), and with
-// round-robin tile ownership those were finished eight tile-times earlier.  So here every CTA runs its phase-1 tiles, swaps
-// the weights, and goes straight on with its phase-2 tiles -- ownership reversed (CTA c takes tile G-1-c + kG), so that
+// round-robin tile ownership those were finished eight tile-times earlier.  So here every CTA runs its phase-1 tiles and goes
+// straight on with its phase-2 tiles (the phase-2 weights are either resident from the start -- PairParams::dual_w, forward
+// pair -- or swapped in once phase 1's MMAs have retired) -- ownership reversed (CTA c takes tile G-1-c + kG), so that
 // the CTAs that owned nine tiles in phase 1 own eight in phase 2: 17 tile-times instead of 18, and ONE fill / drain.
 //
-// Hand-over through global memory: phase-1 epilogue warps TMA-store their slab of tile t, wait for the COMPLETION of that
-// bulk group (not just its shared-memory reads) before they touch the next tile, and then release-increment ready[t]
-// (8 warps per tile).  The phase-2 TMA producer acquire-spins on ready[t-1..t+1] == 8, issues a proxy fence and loads the
-// halo window.  The counters clean themselves: the last of the (up to three) phase-2 tiles that consumed ready[t] resets
-// it, so the buffer (zero-filled once with the workspace) is ready for the next launch.  All CTAs are co-resident (grid <=
+// Hand-over through global memory: phase-1 epilogue warps TMA-store their slab of tile t and bump ready[t] once that bulk
+// group is COMPLETE (not just its shared-memory reads).  Waiting for completion right away would stall the epilogue, so the
+// publication trails the stores by kLag bulk groups (cp.async.bulk.wait_group kLag-1; the tail is flushed after the last
+// tile).  The phase-2 TMA producer polls ready[t-1..t+1] == 8 on three lanes in parallel and then loads the halo window
+// (protocol variants: fence_proxy_async_mode below).  The counters clean themselves: the last of the (up to three) phase-2
+// tiles that consumed ready[t] resets it -- bookkeeping deferred by one tile so it is off the critical path -- so the
+// buffer (zero-filled once with the workspace) is ready for the next launch.  All CTAs are co-resident (grid <=
 // number of SMs, one CTA per SM), so the waits cannot deadlock; a CTA delayed by another stream's kernel delays its
 // neighbours' phase 2 by exactly the time it would have delayed the end of the kernel anyway.
 //

@@ -24,13 +24,14 @@ namespace sres {
 
 constexpr int kConvW = 64 * 64 * 9;  // floats of one 64->64 conv weight
 // bf16 gradient buffers rotate through a ring: a deferred weight-gradient job keeps reading its buffer until its
-// batch (up to 8 jobs = 4 blocks, on the side stream) has RUN, so the ring is two batches deep -- by the time a
-// buffer comes round again the batch that read it was launched >= 4 blocks earlier and the join is free
-constexpr int kRing = 8;
+// batch (8 jobs = 4 blocks by default, on the side stream) has been launched, so the ring holds one batch of blocks
+// plus the block being written (WgQueue::before_write flushes / joins whenever a buffer would be overwritten early,
+// so any ring length is correct -- a short one just cuts the batches short)
+constexpr int kRing = 12;
 static int ring_len() {   // buffers actually rotated through (<= kRing): fewer = better L2 locality, more = deeper batches
   static const int v = [] {
     const char* e = getenv("SRES_RING");
-    int n = e ? atoi(e) : 3;
+    int n = e ? atoi(e) : 5;
     return n < 3 ? 3 : (n > kRing ? kRing : n);
   }();
   return v;
@@ -38,7 +39,10 @@ static int ring_len() {   // buffers actually rotated through (<= kRing): fewer 
 static int wgrad_batch_jobs() {
   static const int v = [] {
     const char* e = getenv("SRES_WGRAD_BATCH");
-    int n = e ? atoi(e) : 4;  // measured on B200: 4 jobs / ring 3 == 8 jobs / ring 5 within noise (28.9-29.4 ms); deeper rings lose L2 locality
+    // Measured on B200 (tools/r2_ab3.sh, interleaved, medians): 4 jobs / ring 3 28.26 ms per step, 8 / 5 27.88, 12 / 7 27.93,
+    // 16 / 9 27.74: a launch costs ~13 us of prologue + accumulator drain + reduce whatever its job count (1 job 22.8 us,
+    // 4 jobs 52.9 us), so eight jobs per launch halve that; deeper still is within noise (and the rings lose L2 locality).
+    int n = e ? atoi(e) : 8;
     return n < 1 ? 1 : (n > SRES_WGRAD_MAX_JOBS ? SRES_WGRAD_MAX_JOBS : n);
   }();
   return v;

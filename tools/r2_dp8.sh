@@ -1,5 +1,5 @@
 #!/bin/bash
-# 8-GPU data-parallel checks and bench variants (one box)
+# N-GPU data-parallel check (tools/dp_check.py) and bench beside the 1-GPU bench on the same box: bash tools/r2_dp8.sh [N]
 N=${1:-8}
 mkdir -p gpurun_out
 LOG=gpurun_out/r2_dp$N.log
@@ -8,9 +8,7 @@ run() { timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 
 run 29511 tools/dp_check.py >> $LOG 2>&1; echo "dp_check exit=$?" >> $LOG
 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline --skip-extras 2>/dev/null | tail -1 > gpurun_out/r2_bench_dp1.json
 run 29512 bench.py --gpus $N --steps 20 --warmup 5 2>/dev/null | grep '"metric"' > gpurun_out/r2_bench_dp$N.json
-SRES_MIN_GRID=1 run 29513 bench.py --gpus $N --steps 20 --warmup 5 --skip-extras 2>/dev/null | grep '"metric"' > gpurun_out/r2_bench_dp${N}_mingrid.json
-NCCL_MAX_NCHANNELS=4 run 29514 bench.py --gpus $N --steps 20 --warmup 5 --skip-extras 2>/dev/null | grep '"metric"' > gpurun_out/r2_bench_dp${N}_nch4.json
 grep -E "RESULT|exit=" $LOG | cut -c1-250
-for f in gpurun_out/r2_bench_dp1.json gpurun_out/r2_bench_dp$N.json gpurun_out/r2_bench_dp${N}_mingrid.json gpurun_out/r2_bench_dp${N}_nch4.json; do
+for f in gpurun_out/r2_bench_dp1.json gpurun_out/r2_bench_dp$N.json; do
   python -c "import json,sys; d=json.load(open('$f')); print('$f', 'ms/step %.3f' % d['ms_per_step'], 'tiles/s %.1f' % d['value'], 'e2e %.1f' % d['e2e']['value'], {k: (round(d[k]['value'],1) if k in d else None) for k in ('infer_region','x8')})"
 done
