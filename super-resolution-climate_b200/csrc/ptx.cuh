@@ -206,6 +206,24 @@ __device__ __forceinline__ constexpr uint32_t sdesc_hi_sw128(uint32_t sbo_bytes)
 __device__ __forceinline__ uint32_t sdesc_lo(uint32_t saddr, uint32_t lbo_bytes) {
   return ((saddr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
 }
+// Ampere-style asynchronous 4-byte copy global -> shared; src_bytes == 0 writes zeros without touching global memory.
+__device__ __forceinline__ void cp_async4_zfill(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Packed fp32 FMA (sm_100: FFMA2): acc.{x,y} = fma(a.{x,y}, s, acc.{x,y}), each half rounded like fmaf.  ptxas folds the
+// duplicated scalar into the instruction's broadcast operand form (FFMA2 Rd, Ra.F32x2, Rs.F32, Rd.F32x2), so one issue slot
+// does two FMAs -- the CUDA-core convolutions at the network's two ends are issue-bound, not HBM-bound.
+__device__ __forceinline__ void ffma2_bcast(float2& acc, const float2& a, float s) {
+  const float2 ss = make_float2(s, s);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(reinterpret_cast<uint64_t&>(acc))
+      : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(ss)));
+}
+
 // Arrive on an mbarrier once all previously issued MMAs of this thread retire.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(

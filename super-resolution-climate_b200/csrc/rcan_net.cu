@@ -535,13 +535,13 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
       { PROF("tail wgrad");
       RC(sres_small_out_wgrad(dout, u_last, B, d.cout, Hh, Wh, Gr + n.tail_w, Gr + n.tail_b, accumulate, ws + n.o_sw_ws,
                               sres_small_wgrad_workspace_bytes(), st)); }
-      PROF("tail dgrad + upsampler bwd + body-tail");
+      { PROF("tail dgrad");
       if (L == 0) {
         RC(sres_conv3x3_small_in(dout, P + n.tail_w, nullptr, B, d.cout, Hh, Wh, 1, 0, dres32, dres16, st));
       } else {
         RC(sres_conv3x3_small_in(dout, P + n.tail_w, nullptr, B, d.cout, Hh, Wh, 1, d.up_factor[L - 1], nullptr,
                                  ws + n.o_du16[L - 1], st));
-      }
+      } }
       for (int i = L - 1; i >= 0; --i) {
         const int f = d.up_factor[i], f2 = f * f;
         const void* cur_in = i > 0 ? (const void*)(ws + n.o_u[i - 1]) : (const void*)(ws + n.o_resb);

@@ -24,63 +24,146 @@ constexpr int kMaxSmallC = 4;
 // ---------------------------------------------------------------------------------------------
 constexpr int kBandRows = 8;
 
+// Wide images are walked in column strips of at most 256 pixels (a multiple of 4), so the staged band stays below 48 KB
+// and two blocks share an SM: with the whole 768-pixel row of the x8 configuration staged (123 KB) one block of 8 warps
+// per SM left the issue slots 48 % busy (ncu, round 2) -- the kernels are instruction-bound, not HBM-bound.
+__host__ __device__ inline int strip_cols(int W) {
+  const int n = (W + 255) / 256;
+  return (((W + n - 1) / n) + 3) & ~3;
+}
+
+// Stage the planar fp32 band rows [y0-1, y0+kBandRows] x columns [x_lo-1, x_lo+S] of image b (zero outside the image) as
+// s[c][r][i], i = column - (x_lo - 1), pitch SWp.  One warp per (channel, row): coalesced, no per-element division.
+// Asynchronous copies (cp.async, zero-fill outside the image): the callers stage item i+1 into the other half of a double
+// buffer while they compute item i -- staged synchronously, the ~40 dependent global loads per thread and item took as
+// long as the item's arithmetic.
 template <int CS>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void stage_band_async(float* s, const float* __restrict__ in, int b, int H, int W, int y0,
+                                                 int x_lo, int SWp) {
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  for (int cr = wrp; cr < CS * (kBandRows + 2); cr += 8) {
+    const int c = cr / (kBandRows + 2), r = cr - c * (kBandRows + 2), yy = y0 - 1 + r;
+    const bool yin = yy >= 0 && yy < H;
+    const float* src = in + (((size_t)b * CS + c) * H + (yin ? yy : 0)) * W;
+    float* dst = s + cr * SWp;
+    for (int i = lane; i < SWp; i += 32) {
+      const int xx = x_lo - 1 + i;
+      const bool ok = yin && xx >= 0 && xx < W;
+      cp_async4_zfill(dst + i, src + (ok ? xx : 0), ok ? 4 : 0);
+    }
+  }
+}
+
+// item -> (image, first band row, first strip column)
+struct BandItem { int b, y0, x_lo; };
+__device__ __forceinline__ BandItem band_item(int item, int bands, int nstrips, int S) {
+  const int strip = item % nstrips, bb = item / nstrips;
+  return BandItem{bb / bands, (bb % bands) * kBandRows, strip * S};
+}
+
+template <int CS>
+__global__ void __launch_bounds__(256, 2)
 conv3x3_small_in_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                         int B, int H, int W, int transposed, int unshuffle, float* __restrict__ out_f32,
                         uint16_t* __restrict__ out_bf16) {
-  extern __shared__ float s_in[];  // [CS][kBandRows+2][W+2]
+  extern __shared__ float s_buf[];  // 2 x [CS][kBandRows+2][S+2]
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   const int n0 = lane * 2;  // two output features
-  float wr[2][CS * 9], br[2];
+  float2 wr[CS * 9], br;   // .x / .y = the thread's two features: packed FMAs (ffma2_bcast)
+  {
+    float wt[2][CS * 9], bt[2];
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    br[j] = (bias && !transposed) ? bias[n0 + j] : 0.f;
+    for (int j = 0; j < 2; ++j) {
+      bt[j] = (bias && !transposed) ? bias[n0 + j] : 0.f;
 #pragma unroll
-    for (int c = 0; c < CS; ++c)
+      for (int c = 0; c < CS; ++c)
 #pragma unroll
-      for (int t = 0; t < 9; ++t)
-        wr[j][c * 9 + t] = transposed ? w[(c * 64 + n0 + j) * 9 + (8 - t)] : w[((n0 + j) * CS + c) * 9 + t];
-  }
-  const int P = W + 1, RP = (H + 1) * P, SW = (W + 3) & ~1;   // even pitch: 8-byte aligned pairs
-  const int bands = (H + 1 + kBandRows - 1) / kBandRows;  // the zero row y == H belongs to the last band
-  auto store = [&](int b, int y, int x, float a0, float a1) {
-    long long oq = (long long)b * RP + (long long)y * P + x;
-    if (unshuffle > 1) {  // PixelUnshuffle(f) store: sub-grid (y%f, x%f), position (y/f, x/f)
-      const int f = unshuffle;
-      const int Pl = W / f + 1, Rl = H / f + 1;
-      const int sub = (y % f) * f + (x % f);
-      oq = (long long)sub * B * Rl * Pl + (long long)b * Rl * Pl + (long long)(y / f) * Pl + (x / f);
+        for (int t = 0; t < 9; ++t)
+          wt[j][c * 9 + t] = transposed ? w[(c * 64 + n0 + j) * 9 + (8 - t)] : w[((n0 + j) * CS + c) * 9 + t];
     }
+    br = make_float2(bt[0], bt[1]);
+#pragma unroll
+    for (int i = 0; i < CS * 9; ++i) wr[i] = make_float2(wt[0][i], wt[1][i]);
+  }
+  const int P = W + 1, RP = (H + 1) * P;
+  const int S = strip_cols(W), nstrips = (W + S - 1) / S, SWp = S + 2;   // even pitch: 8-byte aligned pairs
+  const int bands = (H + 1 + kBandRows - 1) / kBandRows;  // the zero row y == H belongs to the last band
+  const int f = unshuffle > 1 ? unshuffle : 1;
+  const int Pl = W / f + 1, Rl = H / f + 1;
+  // PTL row of pixel (y, x) of image b: plain, or PixelUnshuffle(f): sub-grid (y%f, x%f), position (y/f, x/f)
+  auto row_of = [&](int b, int y, int subx) -> long long {
+    if (f == 1) return (long long)b * RP + (long long)y * P;
+    return ((long long)((y % f) * f + subx) * B + b) * Rl * Pl + (long long)(y / f) * Pl;
+  };
+  auto put = [&](long long oq, float a0, float a1) {
     if (out_f32) *reinterpret_cast<float2*>(out_f32 + oq * 64 + n0) = make_float2(a0, a1);
     if (out_bf16) *reinterpret_cast<uint32_t*>(out_bf16 + oq * 64 + n0) = pack_bf16x2(a0, a1);
   };
-  for (int item = blockIdx.x; item < B * bands; item += gridDim.x) {
-    const int b = item / bands, y0 = (item % bands) * kBandRows;
-    __syncthreads();
-    for (int i = threadIdx.x; i < CS * (kBandRows + 2) * SW; i += blockDim.x) {
-      const int xx = i % SW - 1, yy = (i / SW) % (kBandRows + 2) + y0 - 1, c = i / (SW * (kBandRows + 2));
-      s_in[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(in + (((size_t)b * CS + c) * H + yy) * W + xx) : 0.f;
+  auto store = [&](int b, int y, int x, float a0, float a1) { put(row_of(b, y, x % f) + x / f, a0, a1); };
+  const int n_items = B * bands * nstrips, buf_floats = CS * (kBandRows + 2) * SWp;
+  if ((int)blockIdx.x < n_items) {
+    const BandItem it = band_item(blockIdx.x, bands, nstrips, S);
+    stage_band_async<CS>(s_buf, in, it.b, H, W, it.y0, it.x_lo, SWp);
+  }
+  cp_async_commit();
+  int parity = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, parity ^= 1) {
+    const BandItem it = band_item(item, bands, nstrips, S);
+    const int b = it.b, y0 = it.y0, x_lo = it.x_lo, x_hi = min(W, x_lo + S);
+    const bool last_strip = x_lo + S >= W;
+    const float* s_in = s_buf + parity * buf_floats;
+    __syncthreads();   // every warp is done with the previous item: its buffer is free for the prefetch
+    if (item + (int)gridDim.x < n_items) {
+      const BandItem nx = band_item(item + gridDim.x, bands, nstrips, S);
+      stage_band_async<CS>(s_buf + (parity ^ 1) * buf_floats, in, nx.b, H, W, nx.y0, nx.x_lo, SWp);
     }
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
     const int rows = min(kBandRows, H + 1 - y0);
     if ((W & 3) == 0) {
       // four consecutive positions per step (plus one step per row for the padding column): the 6 inputs a 3-tap row
       // needs come from three aligned 8-byte shared loads, 18 loads feed 144 FMAs instead of 72 scalar loads
-      const int gpr = (W >> 2) + 1;
-      for (int grp = wrp; grp < rows * gpr; grp += 8) {
-        const int yl = grp / gpr, gi = grp - yl * gpr, y = y0 + yl;
-        if (gi == (W >> 2)) { store(b, y, W, 0.f, 0.f); continue; }
-        const int x0 = gi * 4;
-        float a[4][2];
+      // Rows outside, groups inside, row pointers hoisted: the integer work per step (a division by the groups per row,
+      // 64-bit PTL row arithmetic for every store) ran on the same pipe as the FMAs and was 15 % of the instructions.
+      const int ng = (x_hi - x_lo) >> 2;
+      for (int yl = 0; yl < rows; ++yl) {
+        const int y = y0 + yl;
+        if (y == H || (f != 1 && f != 2)) {
+          // the zero row below the image / an unusual unshuffle factor: position by position
+          const int ncol = x_hi - x_lo + (last_strip ? 1 : 0);
+          for (int xr = wrp; xr < ncol; xr += 8) {
+            const int x = x_lo + xr;
+            float2 a = make_float2(0.f, 0.f);
+            if (x != W && y != H) {
+              a = br;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { a[j][0] = (y != H) ? br[0] : 0.f; a[j][1] = (y != H) ? br[1] : 0.f; }
-        if (y != H) {
+              for (int c = 0; c < CS; ++c)
+#pragma unroll
+                for (int t = 0; t < 9; ++t)
+                  ffma2_bcast(a, wr[c * 9 + t], s_in[(c * (kBandRows + 2) + yl + t / 3) * SWp + xr + t % 3]);
+            }
+            store(b, y, x, a.x, a.y);
+          }
+          continue;
+        }
+        // f == 1: positions x0..x0+3 are rows q0 + x0 + j;  f == 2: rows q0 + x0/2 (+1) of sub-grid 0 and q1 + ... of sub-grid 1
+        const long long q0 = row_of(b, y, 0), q1 = f == 2 ? row_of(b, y, 1) : q0;
+        float* const f0 = out_f32 ? out_f32 + q0 * 64 + n0 : nullptr;
+        float* const f1 = out_f32 ? out_f32 + q1 * 64 + n0 : nullptr;
+        uint16_t* const h0 = out_bf16 ? out_bf16 + q0 * 64 + n0 : nullptr;
+        uint16_t* const h1 = out_bf16 ? out_bf16 + q1 * 64 + n0 : nullptr;
+        const float* srow = s_in + yl * SWp;
+        for (int gi = wrp; gi < ng; gi += 8) {
+          const int xr = gi * 4;
+          float2 a[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) a[j] = br;
 #pragma unroll
           for (int c = 0; c < CS; ++c)
 #pragma unroll
             for (int ty = 0; ty < 3; ++ty) {
-              const float* dr = s_in + (c * (kBandRows + 2) + yl + ty) * SW + x0;
+              const float* dr = srow + (c * (kBandRows + 2) + ty) * SWp + xr;
               const float2 d01 = *reinterpret_cast<const float2*>(dr);
               const float2 d23 = *reinterpret_cast<const float2*>(dr + 2);
               const float2 d45 = *reinterpret_cast<const float2*>(dr + 4);
@@ -88,32 +171,36 @@ conv3x3_small_in_kernel(const float* __restrict__ in, const float* __restrict__ 
 #pragma unroll
               for (int tx = 0; tx < 3; ++tx)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  a[j][0] = fmaf(wr[0][c * 9 + ty * 3 + tx], d6[j + tx], a[j][0]);
-                  a[j][1] = fmaf(wr[1][c * 9 + ty * 3 + tx], d6[j + tx], a[j][1]);
-                }
+                for (int j = 0; j < 4; ++j) ffma2_bcast(a[j], wr[c * 9 + ty * 3 + tx], d6[j + tx]);
             }
-        }
+          // element offsets of the four positions from the row pointers (32-bit: a row of the image is < 2^31 elements)
+          const int e0 = f == 2 ? ((x_lo + xr) >> 1) * 64 : (x_lo + xr) * 64;
+          const int step = f == 2 ? 0 : 64;   // f == 2: positions 0/1 share a row of their sub-grids, 2/3 the next one
+          const int e[4] = {e0, e0 + step, e0 + 64 + step, e0 + 64 + 2 * step};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) store(b, y, x0 + j, a[j][0], a[j][1]);
+          for (int j = 0; j < 4; ++j) {
+            const bool odd = f == 2 && (j & 1);
+            if (out_f32) *reinterpret_cast<float2*>((odd ? f1 : f0) + e[j]) = a[j];
+            if (out_bf16) *reinterpret_cast<uint32_t*>((odd ? h1 : h0) + e[j]) = pack_bf16x2(a[j].x, a[j].y);
+          }
+        }
+        if (last_strip && wrp == (ng & 7)) store(b, y, W, 0.f, 0.f);   // the padding column
       }
       continue;
     }
-    for (int pos = wrp; pos < rows * P; pos += 8) {
-      const int yl = pos / P, x = pos - yl * P, y = y0 + yl;
-      float a0 = 0.f, a1 = 0.f;
+    const int ncol = x_hi - x_lo + (last_strip ? 1 : 0);   // + the padding column x == W
+    for (int pos = wrp; pos < rows * ncol; pos += 8) {
+      const int yl = pos / ncol, xr = pos - yl * ncol, x = x_lo + xr, y = y0 + yl;
+      float2 a = make_float2(0.f, 0.f);
       if (x != W && y != H) {
-        a0 = br[0]; a1 = br[1];
+        a = br;
 #pragma unroll
         for (int c = 0; c < CS; ++c)
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            const float v = s_in[(c * (kBandRows + 2) + yl + t / 3) * SW + x + t % 3];
-            a0 = fmaf(wr[0][c * 9 + t], v, a0);
-            a1 = fmaf(wr[1][c * 9 + t], v, a1);
-          }
+          for (int t = 0; t < 9; ++t)
+            ffma2_bcast(a, wr[c * 9 + t], s_in[(c * (kBandRows + 2) + yl + t / 3) * SWp + xr + t % 3]);
       }
-      store(b, y, x, a0, a1);
+      store(b, y, x, a.x, a.y);
     }
   }
 }
@@ -263,93 +350,118 @@ __global__ void small_in_wgrad_reduce_kernel(const float* __restrict__ part, int
 // 128-byte row) and 8 warps walk the band's rows.  Per-block partials, then a fixed-order reduce.
 // ---------------------------------------------------------------------------------------------
 template <int CS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 small_out_wgrad_kernel(const float* __restrict__ dout, const uint16_t* __restrict__ u, int B, int H, int W,
                        float* __restrict__ part) {
-  extern __shared__ float s_d[];  // [CS][kBandRows+2][W+2], then the cross-warp reduction buffer
+  extern __shared__ float s_buf[];  // 2 x [CS][kBandRows+2][S+2] (column strips, see strip_cols), then the cross-warp reduction buffer
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   const int k0 = lane * 2;
-  const int P = W + 1, RP = (H + 1) * P, SW = (W + 3) & ~1;   // even pitch: 8-byte aligned pairs
-  float acc[2][CS * 9];
-  float accb = 0.f;  // bias gradient: lanes < CS of warp 0..7 sum channel `lane`
+  const int P = W + 1, RP = (H + 1) * P;
+  const int S = strip_cols(W), nstrips = (W + S - 1) / S, SWp = S + 2;   // even pitch: 8-byte aligned pairs
+  // With 4 image channels a thread's 2 x 36 accumulators (as 64-bit pairs) do not fit 128 registers beside the operands
+  // (ptxas kept them in local memory across the loop), so the warps split the channels: even warps take channels 0-1, odd
+  // warps 2-3, and each pair of warps walks the same positions (the second read of a U row hits L1).
+  constexpr int kSplit = CS > 3 ? 2 : 1, CL = CS / kSplit, kWalkers = 8 / kSplit;
+  const int c_lo = kSplit == 2 ? (wrp & 1) * CL : 0, walker = kSplit == 2 ? wrp >> 1 : wrp;
+  const bool sums_bias = kSplit == 1 || (wrp & 1) == 0;
+  float2 acc[CL * 9];   // .x / .y = the thread's two input features: packed FMAs (ffma2_bcast)
+  float accb = 0.f;  // bias gradient: lanes < CS sum channel `lane`
 #pragma unroll
-  for (int j = 0; j < 2; ++j)
-#pragma unroll
-    for (int i = 0; i < CS * 9; ++i) acc[j][i] = 0.f;
+  for (int i = 0; i < CL * 9; ++i) acc[i] = make_float2(0.f, 0.f);
   const int bands = (H + kBandRows - 1) / kBandRows;
-  for (int item = blockIdx.x; item < B * bands; item += gridDim.x) {
-    const int b = item / bands, y0 = (item % bands) * kBandRows;
-    __syncthreads();
-    for (int i = threadIdx.x; i < CS * (kBandRows + 2) * SW; i += blockDim.x) {
-      const int xx = i % SW - 1, yy = (i / SW) % (kBandRows + 2) + y0 - 1, c = i / (SW * (kBandRows + 2));
-      s_d[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(dout + (((size_t)b * CS + c) * H + yy) * W + xx) : 0.f;
+  const int n_items = B * bands * nstrips, buf_floats = CS * (kBandRows + 2) * SWp;
+  if ((int)blockIdx.x < n_items) {
+    const BandItem it = band_item(blockIdx.x, bands, nstrips, S);
+    stage_band_async<CS>(s_buf, dout, it.b, H, W, it.y0, it.x_lo, SWp);
+  }
+  cp_async_commit();
+  int parity = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, parity ^= 1) {
+    const BandItem it = band_item(item, bands, nstrips, S);
+    const int b = it.b, y0 = it.y0, x_lo = it.x_lo, x_hi = min(W, x_lo + S);
+    const float* s_d = s_buf + parity * buf_floats;
+    __syncthreads();   // every warp is done with the previous item: its buffer is free for the prefetch
+    if (item + (int)gridDim.x < n_items) {
+      const BandItem nx = band_item(item + gridDim.x, bands, nstrips, S);
+      stage_band_async<CS>(s_buf + (parity ^ 1) * buf_floats, dout, nx.b, H, W, nx.y0, nx.x_lo, SWp);
     }
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
     const int rows = min(kBandRows, H - y0);
+    const float* s_c = s_d + c_lo * (kBandRows + 2) * SWp;   // this warp's channels
     if ((W & 3) == 0) {
       // four consecutive positions per step: the 6 dout values a 3-tap row needs for them come from three aligned
-      // 8-byte shared loads (SW is even), 18 loads feed 144 FMAs -- the scalar path below needs 72
-      const int gpr = W >> 2;
-      for (int grp = wrp; grp < rows * gpr; grp += 8) {
-        const int yl = grp / gpr, x0 = (grp - yl * gpr) * 4;
-        const size_t q = (size_t)b * RP + (size_t)(y0 + yl) * P + x0;
-        float u0[4], u1[4];
+      // 8-byte shared loads (the pitch is even), 18 loads feed 144 FMAs -- the scalar path below needs 72
+      // Rows outside, groups inside (no division per step); the four U rows of the NEXT step are requested before the
+      // FMAs of this one -- issued right before their use, the loads were 44 % of the stall samples (ncu, round 2).
+      const int ng = (x_hi - x_lo) >> 2;
+      for (int yl = 0; yl < rows; ++yl) {
+        const uint16_t* urow = u + ((size_t)b * RP + (size_t)(y0 + yl) * P + x_lo) * 64 + k0;
+        const float* srow = s_c + yl * SWp;
+        uint32_t nxt[4];
+        if (walker < ng) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t uv = *reinterpret_cast<const uint32_t*>(u + (q + j) * 64 + k0);
-          u0[j] = bf16_lo(uv); u1[j] = bf16_hi(uv);
+          for (int j = 0; j < 4; ++j) nxt[j] = *reinterpret_cast<const uint32_t*>(urow + (walker * 4 + j) * 64);
         }
+        for (int gi = walker; gi < ng; gi += kWalkers) {
+          const int xr = gi * 4;
+          float2 uu[4];
 #pragma unroll
-        for (int c = 0; c < CS; ++c)
+          for (int j = 0; j < 4; ++j) uu[j] = make_float2(bf16_lo(nxt[j]), bf16_hi(nxt[j]));
+          if (gi + kWalkers < ng) {
 #pragma unroll
-          for (int ry = 0; ry < 3; ++ry) {
-            const float* dr = s_d + (c * (kBandRows + 2) + yl + ry) * SW + x0;
-            const float2 d01 = *reinterpret_cast<const float2*>(dr);
-            const float2 d23 = *reinterpret_cast<const float2*>(dr + 2);
-            const float2 d45 = *reinterpret_cast<const float2*>(dr + 4);
-            const float d6[6] = {d01.x, d01.y, d23.x, d23.y, d45.x, d45.y};
-            const int ty = 2 - ry;   // smem row yl + 2 - ty
-#pragma unroll
-            for (int tx = 0; tx < 3; ++tx)
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float d = d6[j + 2 - tx];
-                acc[0][c * 9 + ty * 3 + tx] = fmaf(u0[j], d, acc[0][c * 9 + ty * 3 + tx]);
-                acc[1][c * 9 + ty * 3 + tx] = fmaf(u1[j], d, acc[1][c * 9 + ty * 3 + tx]);
-              }
+            for (int j = 0; j < 4; ++j) nxt[j] = *reinterpret_cast<const uint32_t*>(urow + (xr + kWalkers * 4 + j) * 64);
           }
-        if (lane < CS) {
-          const float* dr = s_d + (lane * (kBandRows + 2) + yl + 1) * SW + x0 + 1;
-          accb += (dr[0] + dr[1]) + (dr[2] + dr[3]);
+#pragma unroll
+          for (int c = 0; c < CL; ++c)
+#pragma unroll
+            for (int ry = 0; ry < 3; ++ry) {
+              const float* dr = srow + (c * (kBandRows + 2) + ry) * SWp + xr;
+              const float2 d01 = *reinterpret_cast<const float2*>(dr);
+              const float2 d23 = *reinterpret_cast<const float2*>(dr + 2);
+              const float2 d45 = *reinterpret_cast<const float2*>(dr + 4);
+              const float d6[6] = {d01.x, d01.y, d23.x, d23.y, d45.x, d45.y};
+              const int ty = 2 - ry;   // smem row yl + 2 - ty
+#pragma unroll
+              for (int tx = 0; tx < 3; ++tx)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ffma2_bcast(acc[c * 9 + ty * 3 + tx], uu[j], d6[j + 2 - tx]);
+            }
+          if (sums_bias && lane < CS) {
+            const float* dr = s_d + (lane * (kBandRows + 2) + yl + 1) * SWp + xr + 1;
+            accb += (dr[0] + dr[1]) + (dr[2] + dr[3]);
+          }
         }
       }
       continue;
     }
-    for (int pos = wrp; pos < rows * W; pos += 8) {
-      const int yl = pos / W, x = pos - yl * W;
-      const size_t q = (size_t)b * RP + (size_t)(y0 + yl) * P + x;
+    const int ncol = x_hi - x_lo;
+    for (int pos = walker; pos < rows * ncol; pos += kWalkers) {
+      const int yl = pos / ncol, xr = pos - yl * ncol;
+      const size_t q = (size_t)b * RP + (size_t)(y0 + yl) * P + x_lo + xr;
       const uint32_t uv = *reinterpret_cast<const uint32_t*>(u + q * 64 + k0);
-      const float u0 = bf16_lo(uv), u1 = bf16_hi(uv);
+      const float2 uu = make_float2(bf16_lo(uv), bf16_hi(uv));
 #pragma unroll
-      for (int c = 0; c < CS; ++c)
+      for (int c = 0; c < CL; ++c)
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
+        for (int t = 0; t < 9; ++t)
           // output pixel that sees row p through tap t: (y,x) - (t/3-1, t%3-1); smem index shifts by +1 halo
-          const float d = s_d[(c * (kBandRows + 2) + yl + 2 - t / 3) * SW + x + 2 - t % 3];
-          acc[0][c * 9 + t] = fmaf(u0, d, acc[0][c * 9 + t]);
-          acc[1][c * 9 + t] = fmaf(u1, d, acc[1][c * 9 + t]);
-        }
-      if (lane < CS) accb += s_d[(lane * (kBandRows + 2) + yl + 1) * SW + x + 1];
+          ffma2_bcast(acc[c * 9 + t], uu, s_c[(c * (kBandRows + 2) + yl + 2 - t / 3) * SWp + xr + 2 - t % 3]);
+      if (sums_bias && lane < CS) accb += s_d[(lane * (kBandRows + 2) + yl + 1) * SWp + xr + 1];
     }
   }
-  // cross-warp reduction through shared memory: [8 warps][64 k][kSwAcc]
+  // cross-warp reduction through shared memory: [8 warps][64 k][kSwAcc]; a warp contributes zeros for the channels it
+  // does not own
+  cp_async_wait<0>();
   __syncthreads();
-  float* red = s_d;
+  float* red = s_buf;
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
+    float* mine = red + (wrp * 64 + k0 + j) * kSwAcc;
+    for (int i = 0; i < kSwAcc; ++i) mine[i] = 0.f;
 #pragma unroll
-    for (int i = 0; i < CS * 9; ++i) red[(wrp * 64 + k0 + j) * kSwAcc + i] = acc[j][i];
-    for (int i = CS * 9; i < kSwAcc; ++i) red[(wrp * 64 + k0 + j) * kSwAcc + i] = 0.f;
+    for (int i = 0; i < CL * 9; ++i) mine[c_lo * 9 + i] = j ? acc[i].y : acc[i].x;
   }
   __syncthreads();
   if (lane < CS) red[(wrp * 64 + lane) * kSwAcc + kSwAcc - 1] = accb;
@@ -444,10 +556,10 @@ extern "C" int sres_conv3x3_small_in(const float* in_nchw, const float* w, const
   if (unshuffle > 1 && (H % unshuffle || W % unshuffle))
     return set_error(SRES_ERR_INVALID_ARG, "small_in: unshuffle factor must divide H and W");
   const int bands = (H + 1 + kBandRows - 1) / kBandRows;
-  int blocks = B * bands;
-  if (blocks > small_grid() * 2) blocks = small_grid() * 2;
-  const size_t smem = (size_t)Cs * (kBandRows + 2) * ((W + 3) & ~1) * sizeof(float);
-  if (smem > 200 * 1024) return set_error(SRES_ERR_UNSUPPORTED, "small_in: image too wide");
+  const int S = strip_cols(W), nstrips = (W + S - 1) / S;
+  long long items = (long long)B * bands * nstrips;
+  const int blocks = (int)(items > small_grid() * 2 ? small_grid() * 2 : items);
+  const size_t smem = 2 * (size_t)Cs * (kBandRows + 2) * (S + 2) * sizeof(float);   // double buffer, <= 83 KB
   cudaStream_t st = (cudaStream_t)stream;
   uint16_t* o16 = (uint16_t*)out_bf16;
 #define SRES_LAUNCH_SMALL_IN(CS)                                                                                   \
@@ -512,10 +624,9 @@ extern "C" int sres_small_out_wgrad(const float* dout_nchw, const void* u_bf16, 
   const int grid = small_grid();
   if (workspace_bytes < (size_t)grid * 64 * kSwAcc * sizeof(float))
     return set_error(SRES_ERR_INVALID_ARG, "small_out_wgrad: workspace too small");
-  size_t smem = (size_t)Cs * (kBandRows + 2) * ((W + 3) & ~1) * sizeof(float);
+  size_t smem = 2 * (size_t)Cs * (kBandRows + 2) * (strip_cols(W) + 2) * sizeof(float);   // double buffer
   const size_t red = (size_t)8 * 64 * kSwAcc * sizeof(float);
   if (smem < red) smem = red;
-  if (smem > 200 * 1024) return set_error(SRES_ERR_UNSUPPORTED, "small_out_wgrad: image too wide");
   cudaStream_t st = (cudaStream_t)stream;
   const uint16_t* u16 = (const uint16_t*)u_bf16;
   float* partp = (float*)workspace;
