@@ -42,6 +42,7 @@ struct WgMaps {
 
 struct WgradKParams {
   int P, npos, n_chunks, nstage, xrows, dyrows, njobs, max_split;
+  int xbox, dybox;     // rows per TMA box of the X window / the dY tile (the tensor maps are encoded with these)
   int off_a[kWgAcc];   // row offset (ky*P+kx) of the first tap of each accumulator
   int lbo[kWgAcc];     // byte distance to the second tap's window
   float* part_bias;    // [njobs][max_split][64]
@@ -103,10 +104,10 @@ conv3x3_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
       const int q0 = c * 128;
       if (leader) {
         mbar_expect_tx(&bar_full[slot], stage_bytes);
-        for (int r = 0; r < p.dyrows; r += 64) tma_load_2d(dst + r * 128, tmDY, &bar_full[slot], 0, q0 - dy_row0 + r);
+        for (int r = 0; r < p.dyrows; r += p.dybox) tma_load_2d(dst + r * 128, tmDY, &bar_full[slot], 0, q0 - dy_row0 + r);
         uint8_t* xdst = dst + p.dyrows * 128;
         const int x0 = q0 - (p.P + 1);
-        for (int r = 0; r < p.xrows; r += 64) tma_load_2d(xdst + r * 128, tmX, &bar_full[slot], 0, x0 + r);
+        for (int r = 0; r < p.xrows; r += p.xbox) tma_load_2d(xdst + r * 128, tmX, &bar_full[slot], 0, x0 + r);
       }
       __syncwarp();
     }
@@ -351,8 +352,15 @@ extern "C" int sres_conv3x3_wgrad_batch(const sres_wgrad_job* jobs, int njobs, i
   if (npos > 0x7fffff00LL) return set_error(SRES_ERR_UNSUPPORTED, "wgrad: batch too large");
   p.npos = (int)npos;
   p.n_chunks = (p.npos + 127) / 128;
-  p.xrows = (128 + 2 * (p.P + 1) + 1 + 63) / 64 * 64;
+  // X window: 128 positions + the halo of 2(P+1)+1 rows.  When it fits one TMA box (<= 256 rows) it is loaded exactly
+  // (rounded to the 8-row swizzle period) in ONE copy; wider windows go in 64-row boxes.  The kernel's slope per job is set
+  // by this feed, not by its MMAs (see wgrad_n128_enabled), so the 24 rows the 64-row rounding added at 48 x 48 were 6 % of it.
+  const int xneed = 128 + 2 * (p.P + 1) + 1;
   bool n128 = wgrad_n128_enabled();
+  const bool exact = !n128 && (xneed + 7) / 8 * 8 <= 256 && !getenv("SRES_WGRAD_BOX64");
+  p.xrows = exact ? (xneed + 7) / 8 * 8 : (xneed + 63) / 64 * 64;
+  p.xbox = exact ? p.xrows : 64;
+  p.dybox = exact ? 128 : 64;
   p.dyrows = n128 ? (128 + p.P + 63) / 64 * 64 : 128;
   if (n128 && ((232448 - 1024 - 2048) / ((p.dyrows + p.xrows) * 128) < 1 || p.P * 128 >= (1 << 18))) {
     n128 = false;  // very wide images: the plain scheme needs less shared memory
@@ -400,9 +408,9 @@ extern "C" int sres_conv3x3_wgrad_batch(const sres_wgrad_job* jobs, int njobs, i
   for (int j = 0; j < kWgMaxJobs; ++j) {
     const sres_wgrad_job& J = jobs[j < njobs ? j : 0];
     if (!J.x_bf16 || !J.dy_bf16 || !J.dw_oihw) return set_error(SRES_ERR_INVALID_ARG, "wgrad: null pointer in job");
-    int rc = make_tmap_rows64(&maps.x[j], J.x_bf16, (uint64_t)p.npos, 64);
+    int rc = make_tmap_rows64(&maps.x[j], J.x_bf16, (uint64_t)p.npos, (uint32_t)p.xbox);
     if (rc) return rc;
-    rc = make_tmap_rows64(&maps.dy[j], J.dy_bf16, (uint64_t)p.npos, 64);
+    rc = make_tmap_rows64(&maps.dy[j], J.dy_bf16, (uint64_t)p.npos, (uint32_t)p.dybox);
     if (rc) return rc;
     rj.j[j].dw = J.dw_oihw; rj.j[j].db = J.dbias; rj.j[j].cout_total = J.cout_total; rj.j[j].oc_stride = J.oc_stride;
     rj.j[j].oc_offset = J.oc_offset; rj.j[j].accumulate = J.accumulate;
