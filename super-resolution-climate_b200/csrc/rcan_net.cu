@@ -36,6 +36,12 @@ static int ring_len() {   // buffers actually rotated through (<= kRing): fewer 
   }();
   return v;
 }
+// SRES_JOIN_PER_SEG=1: the round-1 behaviour (join the side stream after every backward segment, squeeze-excite parameter
+// gradients on the main stream) for A/B runs.
+static bool join_per_segment() {
+  static const bool v = [] { const char* e = getenv("SRES_JOIN_PER_SEG"); return e && atoi(e) != 0; }();
+  return v;
+}
 static int wgrad_batch_jobs() {
   static const int v = [] {
     const char* e = getenv("SRES_WGRAD_BATCH");
@@ -484,6 +490,24 @@ struct WgQueue {
     n = 0;
     return rc;
   }
+  // Run one more piece of work that only depends on what the main stream has enqueued so far (the channel-attention
+  // parameter gradients of a finished group) behind the weight-gradient batches on the side stream.
+  template <class F>
+  int run_side(F fn) {
+    if (!ax || join_per_segment()) return fn(st);
+    const int i = ax->next;
+    ax->next = (i + 1) % AsyncCtx::kEvents;
+    RC(wait_slot(i));
+    cudaError_t e = cudaEventRecord(ax->fork[i], (cudaStream_t)st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ax->side, ax->fork[i], 0);
+    if (e != cudaSuccess) return set_cuda_error(e, "backward: fork side stream");
+    RC(fn((void*)ax->side));
+    e = cudaEventRecord(ax->done[i], ax->side);
+    if (e != cudaSuccess) return set_cuda_error(e, "backward: side event");
+    for (int k = 0; k < SRES_WGRAD_MAX_JOBS; ++k) ax->bufs[i][k] = nullptr;
+    ax->live[i] = true;
+    return SRES_OK;
+  }
   int push(const void* x, const void* dy, int B_, int H_, int W_, float* dw, float* db, int cout_total, int stride,
            int offset, int acc, float scale = 1.f) {
     if (n && (B_ != B || H_ != H || W_ != W)) RC(flush());
@@ -564,7 +588,7 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
       RC(wq.before_write(gb16));
       RC(conv64(dres16, WD(n.cidx_bt()), nullptr, B, H, W, st, ga, gb16));
       RC(wq.flush());
-      RC(wq.join_all());
+      if (join_per_segment()) RC(wq.join_all());
     } else if (seg <= G && n.edsr) {
       // ResBlocks R-1..0.  ga = fp32 gradient trunk; its bf16 copy for block r lives in gb16 (r = R-1, written by
       // segment 0) or dt2[r % ring_len()] (written by block r+1's conv1 input-gradient).
@@ -583,7 +607,6 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
         RC(conv64(dt1, WD(n.cidx(0, r, 0)), nullptr, B, H, W, st, ga, nxt, 0, nullptr, ga));
       }
       RC(wq.flush());
-      RC(wq.join_all());
       if (l2hint) RC(sres_l2_persist_window(nullptr, 0, st));
     } else if (seg <= G) {
       const int g = G - seg;
@@ -631,19 +654,27 @@ static int backward(const Net& n, const float* P, const float* x, const float* d
         }
       }
       RC(wq.flush());
-      RC(wq.join_all());
       if (l2hint) RC(sres_l2_persist_window(nullptr, 0, st));
+      // The group's squeeze-excite parameter gradients (20 small latency-bound blocks, 66 us) only read what the
+      // ca_bwd kernels above saved: they go behind the weight-gradient batches on the side stream instead of holding up
+      // the next group's input-gradient chain.
       const long long first = n.off_rcab(g, 0) + 2 * (kConvW + 64);
       PROF("ca_param_grads");
-      RC(sres_ca_param_grads(P + first, Gr + first, n.rcab_sz, R, (const float*)(ws + n.o_mean) + (size_t)g * R * B * 64,
-                             (const float*)(ws + n.o_ds) + (size_t)g * R * B * 64, B, n.hid, accumulate, ws + n.o_ca_scr,
-                             sres_ca_param_grads_scratch_bytes(R, B), st));
+      if (join_per_segment()) RC(wq.join_all());
+      RC(wq.run_side([&](void* s) {
+        return sres_ca_param_grads(P + first, Gr + first, n.rcab_sz, R, (const float*)(ws + n.o_mean) + (size_t)g * R * B * 64,
+                                   (const float*)(ws + n.o_ds) + (size_t)g * R * B * 64, B, n.hid, accumulate,
+                                   ws + n.o_ca_scr, sres_ca_param_grads_scratch_bytes(R, B), s);
+      }));
     } else if (seg == G + 1) {
       PROF("head wgrad");
       RC(sres_small_in_wgrad(ga, dres32, x, B, d.cin, H, W, Gr + n.head_w, Gr + n.head_b, accumulate, ws + n.o_sw_ws,
                              sres_small_wgrad_workspace_bytes(), st));
     }
   }
+  // One join per call, not per segment: the side stream's work only has to be complete when the caller may look at the
+  // gradients (the data-parallel path calls segment by segment and so still joins before each all-reduce).
+  RC(wq.join_all());
   return SRES_OK;
 }
 
