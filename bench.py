@@ -343,12 +343,13 @@ def run_cuda(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    per_step_launches = eng.launches_forward(TILE, TILE) + eng.launches_backward() + 1 + 4 + 1  # + bicubic, loss(sum x2, value, grad), adam
-
     # ---- value: inputs resident in HBM ------------------------------------------------------------
     for i in range(args.warmup):
         step(resident[i % nbuf])
     sync_all()
+    # kernels per step: the forward / backward numbers are COUNTED by the library while it enqueued (or captured) them
+    # (sres_launch_count, read by the engine around its C calls); + bicubic, loss (partial, final, value, grad), Adam
+    per_step_launches = eng.launches_forward(TILE, TILE) + eng.launches_backward() + 1 + 4 + 1
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()

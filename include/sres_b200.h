@@ -53,6 +53,10 @@ SRES_API int sres_abi_version(void);
 SRES_API const char* sres_last_error(void);
 /* Number of SMs of the current device (grid sizing); <0 on error. */
 SRES_API int sres_device_sm_count(void);
+/* Kernels this library has enqueued so far in this process (eager launches and launches recorded into a stream capture
+ * alike; graph replays do not pass through the library and are not counted).  Monotonic; read it before and after a call
+ * to count that call's launches.  Not part of the reference's interface: accounting for bench.py's `gpu_launches`.  */
+SRES_API long long sres_launch_count(void);
 /* L2 residency hints (optional; plain CUDA access-policy windows).  sres_l2_set_aside reserves up to
  * `bytes` of L2 for persisting lines on the current device (process-wide CUDA limit);
  * sres_l2_persist_window marks [base, base+bytes) as persisting for kernels launched on `stream`
@@ -147,7 +151,7 @@ SRES_API int sres_pack_conv_weights(const float* w_oihw, void* out_bf16, int mod
 SRES_API size_t sres_conv_wgrad_workspace_bytes(void);
 /* Several independent weight gradients of the same geometry in ONE launch (split-K CTAs are divided
  * between the jobs; fewer partials per job, one prologue / accumulator drain per batch).            */
-#define SRES_WGRAD_MAX_JOBS 16
+#define SRES_WGRAD_MAX_JOBS 8
 typedef struct sres_wgrad_job {
   const void* x_bf16;      /* conv input, bf16 PTL                                               */
   const void* dy_bf16;     /* gradient of the conv output, bf16 PTL                              */

@@ -135,6 +135,11 @@ int make_tmap_rows64_half(CUtensorMap* out, const void* base, uint64_t nrows, ui
 
 }  // namespace sres
 
+namespace sres {
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace sres
+extern "C" long long sres_launch_count(void) { return sres::g_launches.load(std::memory_order_relaxed); }
 extern "C" int sres_abi_version(void) { return 3; }  // 3: device-side element count of the losses, sres_conv_tile_rows
 extern "C" const char* sres_last_error(void) { return sres::t_err; }
 extern "C" int sres_device_sm_count(void) { return sres::device_sm_count(); }

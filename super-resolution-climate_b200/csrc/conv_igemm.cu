@@ -591,6 +591,7 @@ static cudaError_t launch_conv_kernel(bool pair, void (*kernel)(KArgs...), dim3 
   }
   cfg.attrs = at;
   cfg.numAttrs = n;
+  count_launch();
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 

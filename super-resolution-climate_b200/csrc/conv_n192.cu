@@ -634,6 +634,7 @@ static cudaError_t launch_n192(void (*kernel)(KArgs...), dim3 grid, size_t smem,
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  count_launch();
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 

@@ -657,6 +657,7 @@ extern "C" int sres_conv3x3_pair(const sres_conv_args* a1, const sres_conv_args*
       if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)) != cudaSuccess) return set_cuda_error(e, "conv pair: smem attribute");
       attr_dev = dev;
     }
+    count_launch();
     e = cudaLaunchKernelEx(&cfg, k, tmA1, tmW1, tmO1, tmM1, tmA2, tmW2, tmO16_2, tmM2, tmR32_2, tmO32_2, p);
   } else {
     auto k = conv3x3_pair_kernel<kPMsk | kPO16, kPR32 | kPO32 | kPMsk | kPDot>;
@@ -665,6 +666,7 @@ extern "C" int sres_conv3x3_pair(const sres_conv_args* a1, const sres_conv_args*
       if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)) != cudaSuccess) return set_cuda_error(e, "conv pair: smem attribute");
       attr_dev = dev;
     }
+    count_launch();
     e = cudaLaunchKernelEx(&cfg, k, tmA1, tmW1, tmO1, tmM1, tmA2, tmW2, tmO16_2, tmM2, tmR32_2, tmO32_2, p);
   }
   if (e != cudaSuccess) return set_cuda_error(e, "conv pair: launch");

@@ -343,7 +343,7 @@ extern "C" size_t sres_conv_wgrad_workspace_bytes(void) {
 extern "C" int sres_conv3x3_wgrad_batch(const sres_wgrad_job* jobs, int njobs, int B, int H, int W, void* workspace,
                                         size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (!jobs || njobs < 1 || njobs > kWgMaxJobs) return set_error(SRES_ERR_INVALID_ARG, "wgrad: 1..16 jobs per batch");
+  if (!jobs || njobs < 1 || njobs > kWgMaxJobs) return set_error(SRES_ERR_INVALID_ARG, "wgrad: 1..8 jobs per batch");
   if (!workspace) return set_error(SRES_ERR_INVALID_ARG, "wgrad: null workspace");
   if (B <= 0 || H <= 0 || W <= 0) return set_error(SRES_ERR_INVALID_ARG, "wgrad: bad geometry");
   WgradKParams p{};

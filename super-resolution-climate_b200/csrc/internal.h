@@ -33,6 +33,9 @@ int make_tmap_rows64_half(CUtensorMap* out, const void* base, uint64_t nrows, ui
 bool l2_hint_enabled();  // true after sres_l2_set_aside(bytes > 0)
 bool pdl_enabled();
 int pdl_level();  // SRES_PDL: 0 = off, 1 = tensor-core kernels only, 2 = also the channel-attention kernels (default)
+// Process-wide count of kernels this library has enqueued (eagerly or into a stream capture): sres_launch_count().  The host
+// engine reads it around its forward / backward calls so that bench.py's `gpu_launches` is counted, not derived.
+void count_launch();
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl_if(bool on, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg{};
@@ -42,6 +45,7 @@ cudaError_t launch_pdl_if(bool on, void (*kernel)(KArgs...), dim3 grid, dim3 blo
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = on ? 1 : 0;
+  count_launch();
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 template <typename... KArgs, typename... Args>
@@ -53,6 +57,7 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  count_launch();
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
@@ -68,6 +73,7 @@ int launch_conv_n48(const sres_conv_args* a, cudaStream_t stream);
   do {                                                            \
     cudaError_t e__ = cudaGetLastError();                         \
     if (e__ != cudaSuccess) return sres::set_cuda_error(e__, where); \
+    sres::count_launch();                                         \
   } while (0)
 
 }  // namespace sres

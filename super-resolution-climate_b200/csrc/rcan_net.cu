@@ -27,7 +27,7 @@ constexpr int kConvW = 64 * 64 * 9;  // floats of one 64->64 conv weight
 // batch (8 jobs = 4 blocks by default, on the side stream) has been launched, so the ring holds one batch of blocks
 // plus the block being written (WgQueue::before_write flushes / joins whenever a buffer would be overwritten early,
 // so any ring length is correct -- a short one just cuts the batches short)
-constexpr int kRing = 12;
+constexpr int kRing = 8;
 static int ring_len() {   // buffers actually rotated through (<= kRing): fewer = better L2 locality, more = deeper batches
   static const int v = [] {
     const char* e = getenv("SRES_RING");
@@ -46,7 +46,8 @@ static int wgrad_batch_jobs() {
   static const int v = [] {
     const char* e = getenv("SRES_WGRAD_BATCH");
     // Measured on B200 (tools/r2_ab3.sh, interleaved, medians): 4 jobs / ring 3 28.26 ms per step, 8 / 5 27.88, 12 / 7 27.93,
-    // 16 / 9 27.74: a launch costs ~13 us of prologue + accumulator drain + reduce whatever its job count (1 job 22.8 us,
+    // 16 / 9 27.74 (the 12- and 16-job runs needed > 4 KB of kernel parameters for the tensor maps, which ncu's launch
+    // interception rejects, so the limit stays at 8): a launch costs ~13 us of prologue + accumulator drain + reduce whatever its job count (1 job 22.8 us,
     // 4 jobs 52.9 us), so eight jobs per launch halve that; deeper still is within noise (and the rings lose L2 locality).
     int n = e ? atoi(e) : 8;
     return n < 1 ? 1 : (n > SRES_WGRAD_MAX_JOBS ? SRES_WGRAD_MAX_JOBS : n);

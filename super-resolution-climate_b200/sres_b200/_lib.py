@@ -57,6 +57,7 @@ def lib():
         L = C.CDLL(path)
         L.sres_last_error.restype = C.c_char_p
         L.sres_ptl_rows.restype = C.c_int64
+        L.sres_launch_count.restype = C.c_longlong
         _lib = L
     return _lib
 

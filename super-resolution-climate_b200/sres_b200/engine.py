@@ -126,6 +126,9 @@ class RcanEngine:
         self._packed_version: Dict[Tuple[int, int, int, bool], int] = {}
         self._dirty_token = 0  # bumped by in-place updates torch cannot see (fused Adam)
         self.launches = 0      # kernels of ours enqueued so far (for bench accounting)
+        self._fwd_count: Dict[tuple, int] = {}   # (B, H, W, training) -> kernels of one forward call (counted by the library)
+        self._bwd_count: Dict[tuple, int] = {}   # ((B, H, W, True), seg_begin, seg_end) -> kernels of that backward call
+        self._last_bwd_key = None
         # CUDA graphs: the whole forward (weight re-pack + ~640 kernels) and the whole backward (~1100
         # kernels) of a given batch shape are captured once and replayed -- static shapes, static workspace.
         self.use_graphs = os.environ.get("SRES_CUDA_GRAPHS", "1") != "0"
@@ -207,35 +210,33 @@ class RcanEngine:
             self._packed_version[key] = v
 
     # -- kernels launched per call (our claim for bench.py's gpu_launches) ----------------------
-    def launches_forward(self, H: int, W: int) -> int:
-        G, R = self.nlayers, self.nblocks
-        ups = sum(f * f for f in self.stages)
-        if self.arch == "edsr":
-            return 1 + 2 * R + 1 + ups + 1
-        fused = (H + 1) * (W + 1) >= 128
-        per_rcab = 3 if fused else 4
-        return 1 + G * (R * per_rcab + 1) + 1 + ups + 1
+    # Counted, not derived: the library counts every kernel it enqueues (sres_launch_count, eager and stream-capture alike);
+    # the engine reads the counter around each C call and remembers the number per (shape, segment range), so a graph
+    # replay -- which does not pass through the library -- is credited with what its capture enqueued.
+    def launches_forward(self, H: int, W: int, training: bool = True) -> int:
+        """Kernels of one forward call at the most recently used batch size of this tile shape."""
+        for key in reversed(list(self._fwd_count)):
+            if key[1] == H and key[2] == W and key[3] == bool(training):
+                return self._fwd_count[key]
+        raise L.SresError("launches_forward: no forward of this shape has run yet")
 
     def launches_backward(self) -> int:
-        """Kernels enqueued by one full backward (weight-gradient jobs of one geometry go out in batches of up to
-        SRES_WGRAD_BATCH (default 4, at most 8): one tensor-core kernel + one reduce kernel per batch)."""
-        G, R = self.nlayers, self.nblocks
-        J = min(8, max(1, int(os.environ.get("SRES_WGRAD_BATCH", "4"))))
-        ups_dgrad = sum(f * f for f in self.stages)
-        # segment 0: the up-conv jobs of stage i run at level-i geometry; the body-tail job joins the level-0 batch
-        jobs0 = (self.stages[0] ** 2 if self.stages else 0) + 1
-        seg0_batches = sum(-(-f * f // J) for f in self.stages[1:]) + -(-jobs0 // J)
-        seg0 = 2 + 1 + ups_dgrad + 1 + 2 * seg0_batches                   # tail wgrad(2), tail dgrad, dgrads, bt dgrad
-        if self.arch == "edsr":
-            return seg0 + 2 * R + 2 * (-(-2 * R // J)) + 2                # 2 dgrads per ResBlock, wgrad batches, head wgrad(2)
-        grp_batches = -(-(1 + 2 * R) // J)
-        grp = 1 + R * (1 + 1 + 1) + 2 + 2 * grp_batches                   # gt dgrad, per RCAB ca_bwd + 2 dgrads, ca params(2)
-        return seg0 + G * grp + 2
+        """Kernels of one full backward pass (all segments) of the most recent backward shape."""
+        key = self._last_bwd_key
+        if key is None:
+            raise L.SresError("launches_backward: no backward has run yet")
+        nseg = self.num_segments()
+        whole = self._bwd_count.get((key, 0, nseg))
+        if whole is not None:
+            return whole
+        return sum(self._bwd_count[(key, s, s + 1)] for s in range(nseg))
 
     # -- forward / backward ---------------------------------------------------------------------
     def _launch_forward(self, key, x, out, ws, always_pack=False):
         B, H, W, training = key
         st = L.cur_stream()
+        n0 = self.lib.sres_launch_count()
+        self._fwd_count.pop(key, None)   # most recently used last
         if always_pack:
             L.check(self.lib.sres_rcan_pack_weights(C.byref(self.desc(B, H, W)), L.ptr(self.flat), L.ptr(ws),
                                                     int(training), st), "sres_rcan_pack_weights")
@@ -243,6 +244,7 @@ class RcanEngine:
             self._ensure_packed(key, ws, st)
         L.check(self.lib.sres_rcan_forward(C.byref(self.desc(B, H, W)), L.ptr(self.flat), L.ptr(x), L.ptr(out),
                                            L.ptr(ws), int(training), st), "sres_rcan_forward")
+        self._fwd_count[key] = self.lib.sres_launch_count() - n0
 
     def forward(self, x: torch.Tensor, training: bool) -> torch.Tensor:
         if x.device != self.device:
@@ -272,7 +274,7 @@ class RcanEngine:
                         self._launch_forward(key, xs, outs, ws, always_pack=True)
                     self._graphs[("fwd", key)] = dict(graph=graph, x=xs, out=outs)
         self._fwd_generation[key] = self._fwd_generation.get(key, 0) + 1
-        self.launches += self.launches_forward(H, W)
+        self.launches += self._fwd_count[key]
         return out
 
     def forward_generation(self, B, H, W) -> int:
@@ -289,9 +291,12 @@ class RcanEngine:
 
     def _launch_backward(self, key, x, dout, accumulate, seg_begin, seg_end):
         B, H, W, _ = key
+        n0 = self.lib.sres_launch_count()
         L.check(self.lib.sres_rcan_backward(C.byref(self.desc(B, H, W)), L.ptr(self.flat), L.ptr(x), L.ptr(dout),
                                             L.ptr(self.flat_grad), int(accumulate), L.ptr(self._ws[key]),
                                             seg_begin, seg_end, self._async, L.cur_stream()), "sres_rcan_backward")
+        self._bwd_count[(key, seg_begin, seg_end)] = self.lib.sres_launch_count() - n0
+        self._last_bwd_key = key
 
     def backward(self, x: torch.Tensor, dout: torch.Tensor, accumulate: bool, seg_begin: int = 0,
                  seg_end: Optional[int] = None):

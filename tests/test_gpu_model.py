@@ -361,6 +361,45 @@ def test_loss_decreases_when_training(dev):
     assert np.isfinite(losses).all() and losses[-1] < 0.7 * losses[0]
 
 
+def test_launch_accounting_is_counted_by_the_library(dev):
+    """bench.py's `gpu_launches` comes from the library's own launch counter (sres_launch_count), read by the engine
+    around its C calls.  Two residual groups of two RCABs, 48-px tiles: the fused two-convolution launches are in use, so a
+    forward is head + 2 x (2 x (pair + channel attention) + group tail) + body tail + 4 + 4 up-convs + tail = 21 kernels
+    once the packed weights are current, and a graph replay is credited with what its capture enqueued (that many plus
+    the weight re-pack).  The counter moves by exactly what the engine reports."""
+    from sres_b200 import nn as snn, _lib as L
+    cfg = O.model_cfg(nlayers=2, nblocks=2)
+    torch.manual_seed(0)
+    model = _build(cfg, 2, dev)
+    eng = model.engine
+    hr = synth_hr(4, 2, 192, smooth=True).to(dev)
+    lr_in = snn.bicubic_resize(hr, 0.25)
+    lib = L.lib()
+    counted = []
+    for it in range(4):
+        n0, e0 = lib.sres_launch_count(), eng.launches
+        model.zero_grad()
+        loss = snn.loss(model(lr_in.requires_grad_(True)), hr, "l2")
+        fwd = eng.launches - e0
+        loss.backward()
+        torch.cuda.synchronize()
+        counted.append((fwd, eng.launches - e0 - fwd, lib.sres_launch_count() - n0))
+    if eng.use_graphs:
+        assert counted[-1][0] == eng.launches_forward(48, 48) > 21        # a replay: the forward kernels + the weight re-pack
+    else:
+        assert all(f == 21 for f, _, _ in counted[1:])                    # packed weights are current after the first call
+    assert counted[-1][1] == eng.launches_backward() > 0
+    # what went through the library per iteration: the 4 loss kernels always; eager mode adds every forward and backward;
+    # graph mode enqueues the forward twice in iteration 0 (eager call, then its capture), the backward eagerly in
+    # iteration 0 and into its capture in iteration 1, and nothing but the loss afterwards (replays)
+    f, b = counted[-1][0], counted[-1][1]
+    through_lib = [c for _, _, c in counted]
+    if eng.use_graphs:
+        assert through_lib == [2 * f + b + 4, b + 4, 4, 4], counted
+    else:
+        assert through_lib[1:] == [f + b + 4] * 3, counted
+
+
 def test_full_size_training_is_stable(dev):
     """RCAN-full x4 at the benchmark batch (64 tiles of 2x48x48), 40 optimiser steps on a fixed smooth batch through
     the graph-replayed path (side-stream weight gradients, PDL, fused Adam): the loss stays finite and goes down."""
