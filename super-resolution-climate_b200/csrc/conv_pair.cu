@@ -6,8 +6,8 @@
 // MMAs with nothing to overlap) and drain (the last tile's epilogue) -- together about a third of the kernel.  The second
 // convolution of a pair needs, for its tile t, only tiles t-1, t, t+1 of the first (the halo is P+1 <= 128 rows), and with
 // round-robin tile ownership those were finished eight tile-times earlier.  So here every CTA runs its phase-1 tiles and goes
-// straight on with its phase-2 tiles (the phase-2 weights are either resident from the start -- PairParams::dual_w, forward
-// pair -- or swapped in once phase 1's MMAs have retired) -- ownership reversed (CTA c takes tile G-1-c + kG), so that
+// straight on with its phase-2 tiles (the phase-2 weights have their own region -- PairParams::dual_w, forward pair, see
+// pair_slot -- or are swapped in once phase 1's MMAs have retired) -- ownership reversed (CTA c takes tile G-1-c + kG), so that
 // the CTAs that owned nine tiles in phase 1 own eight in phase 2: 17 tile-times instead of 18, and ONE fill / drain.
 //
 // Hand-over through global memory: phase-1 epilogue warps TMA-store their slab of tile t and bump ready[t] once that bulk
@@ -47,7 +47,9 @@ struct PairParams {
   unsigned* consumed;      // [n_tiles] phase-2 tiles that have seen ready[t]
   long long* timeline;     // bring-up only: per-CTA clock stamps [grid][16]
   int fence_mode;          // proxy fence around the global hand-over (see fence_proxy_async_mode)
-  int dual_w;              // 1: the phase-2 weights have their own 72 KB of shared memory and are loaded at kernel start
+  int dual_w;              // 0: one 72 KB weight region, swapped between the phases; 1: both weight sets resident from the
+                           // start; 2: two regions, and the one a phase does not need lends its space to the halo ring
+                           // (see pair_slot)
 };
 
 constexpr int kPO16 = 1, kPO32 = 2, kPR32 = 4, kPMsk = 8, kPRelu = 16, kPPool = 32, kPDot = 64;
@@ -227,6 +229,34 @@ __device__ __forceinline__ void epi_frag(const PairParams& p, EpiWarp& w, const 
   dst[4 * 64] = all1 ? t0 : t1;
 }
 
+// Which halo-ring slot the i-th tile of a phase uses, and how often that slot has been used before (mbarrier parity).
+//
+// Plain modes (dual_w 0 / 1): slot = it % nstage over the whole launch.
+//
+// Lending mode (dual_w 2, the forward pair): with both 72 KB weight regions the ring has only two slots of its own (B0, B1) --
+// one tile of prefetch, and the MMA warp waited for TMA 10 % of the time.  But phase 1 does not need the phase-2 weights'
+// region and phase 2 does not need phase 1's, and a region holds two slots: phase 1 cycles through X0 X1 B0 B1 (X in the
+// phase-2 weight region) for all but its last two tiles, which use B0 B1 only; once X0 / X1 are released for the last time
+// the phase-2 weights are loaded there, two tile-times before they are needed.  Phase 2 starts on B0 B1 and, from its third
+// tile on, cycles B0 B1 Y0 Y1 (Y in the phase-1 weight region, free once the last phase-1 MMA has retired -- which the
+// producer has seen by then: it waited for B1's release by the last phase-1 tile).  Physical slots: 0 1 = B, 2 3 = X, 4 5 = Y.
+// (The sequence and the use counts below were checked on the host against a running count for every n1, n2 < 60.)
+struct SlotUse { int slot; uint32_t use; };
+__device__ __forceinline__ SlotUse pair_slot(int mode, int nstage, int phase, int i, int it, int n1) {
+  if (mode != 2) return SlotUse{it % nstage, uint32_t(it / nstage)};
+  if (phase == 0) {
+    if (i >= n1 - 2) {
+      const int sl = i - (n1 - 2);                                        // B0 (if n1 >= 2), then B1
+      return SlotUse{sl, uint32_t((n1 - 2 + sl) / 4)};
+    }
+    const int m = (n1 - 3 - i) & 3;                                        // distance from the last lent tile
+    return SlotUse{m == 0 ? 3 : m == 1 ? 2 : m == 2 ? 1 : 0, uint32_t(i >> 2)};
+  }
+  const int m = i & 3;
+  const uint32_t b0 = n1 >= 2 ? uint32_t((n1 - 2) / 4 + 1) : 0u, b1 = n1 >= 1 ? uint32_t((n1 - 1) / 4 + 1) : 0u;   // phase-1 uses
+  return SlotUse{m == 0 ? 0 : m == 1 ? 1 : m == 2 ? 4 : 5, uint32_t(i >> 2) + (m == 0 ? b0 : m == 1 ? b1 : 0u)};
+}
+
 template <int FL1, int FL2>
 __global__ void __launch_bounds__(kPThreads, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW1,
@@ -241,6 +271,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
   uint8_t* smem_w2 = smem + (p.dual_w ? kPWBytes : 0);
   uint8_t* smem_a = smem + kPWBytes * (p.dual_w ? 2 : 1);
   const int stage_bytes = p.stage_rows * 128;
+  // byte offset of a physical ring slot from smem_a (slots 2..5 exist in lending mode only and lie in the weight regions)
+  auto slot_off = [&](int slot) -> int {
+    if (slot < 2 || p.dual_w != 2) return slot * stage_bytes;
+    return (slot < 4 ? kPWBytes + (slot - 2) * stage_bytes : (slot - 4) * stage_bytes) - 2 * kPWBytes;
+  };
   uint8_t* tail = smem + p.off_tail;
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(tail);   // [kPStages]
   uint64_t* bar_empty = bar_full + kPStages;                // [kPStages]
@@ -302,7 +337,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
     if (leader) {
       mbar_expect_tx(&bar_w[0], kPWBytes);
       for (int t = 0; t < 9; ++t) tma_load_2d(smem_w + t * 64 * 128, &tmW1, &bar_w[0], 0, t * 64);
-      if (p.dual_w) {   // room for both weight sets: no swap between the phases
+      if (p.dual_w == 1) {   // room for both weight sets: no swap between the phases
         mbar_expect_tx(&bar_w[1], kPWBytes);
         for (int t = 0; t < 9; ++t) tma_load_2d(smem_w2 + t * 64 * 128, &tmW2, &bar_w[1], 0, t * 64);
       }
@@ -310,14 +345,28 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
     pdl_wait();
     int it = 0;
     for (int tile = c1; tile < p.n_tiles; tile += G, ++it) {
-      const int slot = it % p.nstage;
-      const uint32_t ph = (it / p.nstage) & 1;
+      const SlotUse su = pair_slot(p.dual_w, p.nstage, 0, it, it, n1);
+      const int slot = su.slot;
+      const uint32_t ph = su.use & 1;
       mbar_wait(&bar_empty[slot], ph ^ 1, 1);
       const int row0 = tile * 128 - (p.P + 1);
-      uint8_t* dst = smem_a + slot * stage_bytes;
+      uint8_t* dst = smem_a + slot_off(slot);
       if (leader) {
         mbar_expect_tx(&bar_full[slot], stage_bytes);
         for (int r = 0; r < p.stage_rows; r += p.box_rows) tma_load_2d(dst + r * 128, &tmA1, &bar_full[slot], 0, row0 + r);
+      }
+      __syncwarp();
+    }
+    if (p.dual_w == 2) {
+      // lending mode: the phase-2 weights go where the lent slots X0 / X1 were, once phase 1 has released them for the last
+      // time (X0 was used n1 / 4 times, X1 (n1 + 1) / 4 times) -- its last two tiles are still running on B0 / B1
+      const int ux0 = n1 / 4, ux1 = (n1 + 1) / 4;
+      if (ux0 > 0) mbar_wait(&bar_empty[2], uint32_t(ux0 - 1) & 1, 7);
+      if (ux1 > 0) mbar_wait(&bar_empty[3], uint32_t(ux1 - 1) & 1, 7);
+      PSTAMP(2);   // lent slots released
+      if (leader) {
+        mbar_expect_tx(&bar_w[1], kPWBytes);
+        for (int t = 0; t < 9; ++t) tma_load_2d(smem_w2 + t * 64 * 128, &tmW2, &bar_w[1], 0, t * 64);
       }
       __syncwarp();
     }
@@ -337,7 +386,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
     // ahead of the tensor core (the first version did six dependent global round trips per tile on one lane and made
     // phase 2 producer-bound: +14 us per launch).
     int prev_t = -1;          // the phase-1 tile this lane watched for the previous phase-2 tile
-    for (int tile = c2; tile < p.n_tiles; tile += G, ++it) {
+    for (int tile = c2, i2 = 0; tile < p.n_tiles; tile += G, ++it, ++i2) {
       // lanes 4..6 watch (never the elected lane: a gpu-scope acquire on the thread that has TMA loads in flight waits for
       // those loads and stops the producer from running ahead of the tensor core)
       const int t = tile - 1 + (lane - 4);
@@ -363,11 +412,12 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
       if (tl && lane == 4) tl[12] += clock64() - f0;   // producer: flag bookkeeping + spinning, phase 2
       // (the watchers' acquires and proxy fences are ordered before the elected lane's TMA load by the warp barrier above;
       // the elected lane itself issues no fence: it would wait for its own TMA loads in flight)
-      const int slot = it % p.nstage;
-      const uint32_t ph = (it / p.nstage) & 1;
+      const SlotUse su = pair_slot(p.dual_w, p.nstage, 1, i2, it, n1);
+      const int slot = su.slot;
+      const uint32_t ph = su.use & 1;
       mbar_wait(&bar_empty[slot], ph ^ 1, 1);
       const int row0 = tile * 128 - (p.P + 1);
-      uint8_t* dst = smem_a + slot * stage_bytes;
+      uint8_t* dst = smem_a + slot_off(slot);
       if (leader) {
         mbar_expect_tx(&bar_full[slot], stage_bytes);
         for (int r = 0; r < p.stage_rows; r += p.box_rows) tma_load_2d(dst + r * 128, &tmA2, &bar_full[slot], 0, row0 + r);
@@ -393,9 +443,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
       tc_fence_after();
       if (phase == 1) w_lo = sdesc_lo(smem_u32(smem_w2), 16);
       PSTAMP(3 + 3 * phase);   // weights of this phase landed
-      for (int tile = phase ? c2 : c1; tile < p.n_tiles; tile += G, ++it) {
-        const int slot = it % p.nstage;
-        const uint32_t ph = (it / p.nstage) & 1;
+      for (int tile = phase ? c2 : c1, ip = 0; tile < p.n_tiles; tile += G, ++it, ++ip) {
+        const SlotUse su = pair_slot(p.dual_w, p.nstage, phase, ip, it, n1);
+        const int slot = su.slot;
+        const uint32_t ph = su.use & 1;
         const int acc = it % kPAcc;
         const uint32_t aph = (it / kPAcc) & 1;
         long long w0 = 0, w1 = 0;
@@ -405,7 +456,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
         mbar_wait(&bar_full[slot], ph, 4);
         if (tl && lane == 0) { tl[14] += w1 - w0; tl[15] += clock64() - w1; }   // MMA warp waiting for the epilogue / for TMA
         tc_fence_after();
-        const uint32_t a_tile = a_lo0 + uint32_t(slot * stage_bytes) / 16;
+        const uint32_t a_tile = p.dual_w == 2 ? sdesc_lo(smem_u32(smem_a) + slot_off(slot), 16) : a_lo0 + uint32_t(slot * stage_bytes) / 16;
         const uint32_t d_tmem = tmem_base + uint32_t(acc * 64);
         if (leader) {
 #pragma unroll
@@ -548,18 +599,22 @@ static bool pair_plan(int W, bool fwd, PairParams* p, size_t* smem_bytes) {
   const int rows = 128 + 2 * (W + 2);
   const int box = (rows + 7) / 8 * 8 <= 256 ? (rows + 7) / 8 * 8 : 64;   // the whole window as one TMA box when it fits
   const int stage_rows = (rows + box - 1) / box * box;
-  static const int dual_env = [] { const char* e = getenv("SRES_PAIR_DUALW"); return e ? atoi(e) : 1; }();
+  static const int dual_env = [] { const char* e = getenv("SRES_PAIR_DUALW"); return e ? atoi(e) : 2; }();
   int dual = 0;
   int ns = (smem_max - 1024 - kPWBytes - 1024 - slab) / (stage_rows * 128);
-  if (dual_env) {   // both weight sets resident when that still leaves a ring of dual_env + 1 slots or more
+  if (dual_env) {   // two weight regions when that still leaves a ring of two slots or more
     const int ns2 = (smem_max - 1024 - 2 * kPWBytes - 1024 - slab) / (stage_rows * 128);
-    if (ns2 >= 2 && ns2 >= dual_env + 1) { dual = 1; ns = ns2; }
+    if (ns2 >= 2) {
+      // 2 (default): the region a phase does not need lends two slots to the ring (pair_slot); 1: both weight sets resident
+      dual = (dual_env >= 2 && 2 * stage_rows * 128 <= kPWBytes) ? 2 : 1;
+      ns = dual == 2 ? 2 : ns2;
+    }
   }
   if (ns > kPStages) ns = kPStages;
   if (ns < 2) return false;
   if (p) {
     p->box_rows = box; p->stage_rows = stage_rows; p->nstage = ns; p->dual_w = dual;
-    int off = kPWBytes * (dual ? 2 : 1) + ns * stage_rows * 128;
+    int off = kPWBytes * (dual ? 2 : 1) + ns * stage_rows * 128;   // (lending mode: 2 ring slots of its own, 4 more inside the weight regions)
     p->off_s16 = off; off += 16384;
     p->off_msk = off; off += fwd ? 0 : 16384;
     p->off_s32 = off; off += fwd ? 0 : 32768;
