@@ -203,6 +203,15 @@ SRES_API int sres_ca_apply_fwd(const void* t2_bf16, const float* pool_part, cons
                                const float* b1, const float* w2, const float* b2, int hidden, const float* x_in,
                                float* x_out, void* xb_out_bf16, float* save_mean, float* save_s, int B, int H, int W,
                                void* stream);
+/* the same with the trunk value carried as a bf16 pair x = hi + lo (hi = bf16(x) is the copy the next convolution
+ * reads, lo = bf16(x - hi)): 98 instead of 118 MB per call at B = 64.  Input: either x_in_f32 (a residual group's
+ * first block, network.py:74-77) or xhi_in_bf16 + xlo_in_bf16; output xhi_out_bf16 (must not alias xhi_in) and
+ * xlo_out_bf16 (may alias xlo_in).                                                                              */
+SRES_API int sres_ca_apply_fwd_split(const void* t2_bf16, const float* pool_part, const float* pool_sum, const float* w1,
+                                     const float* b1, const float* w2, const float* b2, int hidden, const float* x_in_f32,
+                                     const void* xhi_in_bf16, const void* xlo_in_bf16, void* xhi_out_bf16,
+                                     void* xlo_out_bf16, float* save_mean, float* save_s, int B, int H, int W,
+                                     void* stream);
 /* backward of the above w.r.t. t2: dt2 (bf16 PTL) from the fp32 trunk gradient; saves ds [B][64];
  * ds_part: scratch [B][sres_ca_blocks_per_image][64] floats                                       */
 SRES_API int sres_ca_bwd(const float* grad_f32, const void* t2_bf16, const float* w1, const float* b1,

@@ -38,6 +38,16 @@ static int ring_len() {   // buffers actually rotated through (<= kRing): fewer 
 }
 // SRES_JOIN_PER_SEG=1: the round-1 behaviour (join the side stream after every backward segment, squeeze-excite parameter
 // gradients on the main stream) for A/B runs.
+// SRES_TRUNK_SPLIT=1 (opt-in): inside a residual group the forward trunk value travels as a bf16 pair (hi = the bf16 copy
+// the next convolution reads anyway, lo = bf16(x - hi)) instead of an fp32 tensor next to that copy: the channel-attention
+// apply kernel moves 98 instead of 118 MB per RCAB (ca.cu).  Measured on B200 (round 2, tools/r2_split.sh): the kernel
+// alone is NOT faster (18.1 vs 17.1 us L2-warm, 24.4 vs 25.9 us cold: the extra unpack / subtract / convert instructions
+// cost what the bytes save) and the training step is slower (28.07 vs 27.47 ms): the fp32 trunk sits in the persisting
+// part of L2, the pair's hi half is an ordinary saved activation that competes with T1 / T2 for the rest.  Default off.
+static bool trunk_split() {
+  static const bool v = [] { const char* e = getenv("SRES_TRUNK_SPLIT"); return e && atoi(e) != 0; }();
+  return v;
+}
 static bool join_per_segment() {
   static const bool v = [] { const char* e = getenv("SRES_JOIN_PER_SEG"); return e && atoi(e) != 0; }();
   return v;
@@ -361,7 +371,8 @@ static int forward(const Net& n, const float* P, const float* x, float* out, uin
   float* pool_sum = (float*)(ws + n.o_pool_sum);
   int xbi = 0;  // index of the bf16 copy of the current trunk value
   const bool l2hint = l2_hint_enabled();
-  if (l2hint) RC(sres_l2_persist_window(xf, (size_t)n.lvRows[0] * 256, st));
+  const bool split = trunk_split() && !n.edsr;
+  if (l2hint) RC(sres_l2_persist_window(xf, (size_t)n.lvRows[0] * (split ? 128 : 256), st));
   { PROF("head conv"); RC(sres_conv3x3_small_in(x, P + n.head_w, P + n.head_b, B, d.cin, H, W, 0, 0, hf, XB(0), st)); }
   const float* gin = hf;
   if (n.edsr) {
@@ -393,8 +404,13 @@ static int forward(const Net& n, const float* P, const float* x, float* out, uin
       float* mean = (float*)(ws + n.o_mean) + (size_t)(training ? ti : 0) * B * 64;
       float* sv = (float*)(ws + n.o_s) + (size_t)(training ? ti : 0) * B * 64;
       { PROF("ca_apply_fwd");
-      RC(sres_ca_apply_fwd(T2(ti), fused_pool ? pool_part : nullptr, fused_pool ? nullptr : pool_sum, w1, b1, w2, b2,
-                           n.hid, r == 0 ? gin : xf, xf, XB(xbi + 1), mean, sv, B, H, W, st)); }
+      if (split)   // xf's storage holds the bf16 low halves (first lvRows * 128 bytes)
+        RC(sres_ca_apply_fwd_split(T2(ti), fused_pool ? pool_part : nullptr, fused_pool ? nullptr : pool_sum, w1, b1, w2, b2,
+                                   n.hid, r == 0 ? gin : nullptr, r == 0 ? nullptr : XB(xbi), r == 0 ? nullptr : (const void*)xf,
+                                   XB(xbi + 1), xf, mean, sv, B, H, W, st));
+      else
+        RC(sres_ca_apply_fwd(T2(ti), fused_pool ? pool_part : nullptr, fused_pool ? nullptr : pool_sum, w1, b1, w2, b2,
+                             n.hid, r == 0 ? gin : xf, xf, XB(xbi + 1), mean, sv, B, H, W, st)); }
       ++xbi;
     }
     const float* pg = P + n.off_gt(g);

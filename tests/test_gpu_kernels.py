@@ -475,6 +475,52 @@ def test_channel_attention_forward_backward(env, B, H, W, red):
     assert rel_l2(gflat.cpu(), ref_flat) < 1e-4
 
 
+@pytest.mark.parametrize("B,H,W,red", [(3, 20, 24, 2), (2, 48, 48, 16)])
+def test_channel_attention_split_trunk_equals_fp32_trunk(env, B, H, W, red):
+    """sres_ca_apply_fwd_split (trunk as a bf16 pair hi + lo) against sres_ca_apply_fwd (fp32 trunk), two chained RCAB
+    residual updates (network.py:61-64): hi is bit-for-bit the fp32 kernel's bf16 copy of the same input, hi + lo is the
+    fp32 value to 2^-17, and both stay zero on the padding rows."""
+    L, lib, dev = env
+    hid = 64 // red
+    w1, b1 = (torch.randn(hid, 64) * 0.3).to(dev), torch.randn(hid).to(dev)
+    w2, b2 = (torch.randn(64, hid) * 0.3).to(dev), torch.randn(64).to(dev)
+    x0 = to_ptl((torch.randn(B, 64, H, W) * 3).to(dev), torch.float32)
+    rows = x0.shape[0]
+    mean, sv = torch.empty(B, 64, device=dev), torch.empty(B, 64, device=dev)
+    mean2, sv2 = torch.empty(B, 64, device=dev), torch.empty(B, 64, device=dev)
+    pool_sum = torch.empty(B, 64, device=dev)
+    st = L.cur_stream()
+    x_f32 = x0                      # fp32 trunk fed to the fp32 kernel
+    hi = lo = None
+    for step in range(2):
+        t2p = to_ptl(bf16_round(torch.randn(B, 64, H, W)).to(dev), torch.bfloat16)
+        L.check(lib.sres_ca_pool(ptr(t2p), ptr(pool_sum), B, H, W, st), "ca_pool")
+        xin = x_f32 if step == 0 else (hi.float() + lo.float())    # the value the pair represents (before lo is overwritten)
+        hi_out = torch.full((rows, 64), 7.0, device=dev, dtype=torch.bfloat16)
+        lo_out = lo if lo is not None else torch.full((rows, 64), 7.0, device=dev, dtype=torch.bfloat16)   # in place from step 1 on
+        L.check(lib.sres_ca_apply_fwd_split(ptr(t2p), None, ptr(pool_sum), ptr(w1), ptr(b1), ptr(w2), ptr(b2), hid,
+                                            ptr(x0) if step == 0 else None, None if step == 0 else ptr(hi), None if step == 0 else ptr(lo),
+                                            ptr(hi_out), ptr(lo_out), ptr(mean), ptr(sv), B, H, W, st), "ca_apply_fwd_split")
+        # the fp32 kernel on the same value
+        xo = torch.full((rows, 64), float("nan"), device=dev)
+        xb = torch.zeros(rows, 64, device=dev, dtype=torch.bfloat16)
+        L.check(lib.sres_ca_apply_fwd(ptr(t2p), None, ptr(pool_sum), ptr(w1), ptr(b1), ptr(w2), ptr(b2), hid, ptr(xin), ptr(xo), ptr(xb),
+                                      ptr(mean2), ptr(sv2), B, H, W, st), "ca_apply_fwd")
+        torch.cuda.synchronize()
+        assert torch.equal(hi_out.view(torch.int16), xb.view(torch.int16))
+        assert torch.equal(mean, mean2) and torch.equal(sv, sv2)
+        pair = hi_out.float() + lo_out.float()
+        err = (pair - xo).abs()
+        assert bool((err <= xo.abs() * 2.0 ** -17 + 1e-30).all()), float((err / (xo.abs() + 1e-30)).max())
+        assert pads_are_zero(hi_out, B, H, W) and pads_are_zero(lo_out, B, H, W)
+        hi, lo = hi_out, lo_out
+    # argument errors are reported, not guessed around
+    assert lib.sres_ca_apply_fwd_split(ptr(t2p), None, ptr(pool_sum), ptr(w1), ptr(b1), ptr(w2), ptr(b2), hid, ptr(x0), ptr(hi), ptr(lo),
+                                       ptr(hi_out), ptr(lo_out), ptr(mean), ptr(sv), B, H, W, st) != 0
+    assert lib.sres_ca_apply_fwd_split(ptr(t2p), None, ptr(pool_sum), ptr(w1), ptr(b1), ptr(w2), ptr(b2), hid, None, ptr(hi), None,
+                                       ptr(hi_out), ptr(lo_out), ptr(mean), ptr(sv), B, H, W, st) != 0
+
+
 def test_bicubic_matches_interpolate(env):
     L, lib, dev = env
     from sres_b200 import nn as snn
