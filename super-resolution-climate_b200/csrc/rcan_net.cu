@@ -22,6 +22,9 @@
 
 namespace sres {
 
+#ifndef SRES_RCAB_CHAIN_DEFAULT
+#define SRES_RCAB_CHAIN_DEFAULT 0
+#endif
 constexpr int kConvW = 64 * 64 * 9;  // floats of one 64->64 conv weight
 // bf16 gradient buffers rotate through a ring: a deferred weight-gradient job keeps reading its buffer until its
 // batch (8 jobs = 4 blocks by default, on the side stream) has been launched, so the ring holds one batch of blocks
@@ -47,6 +50,13 @@ static int ring_len() {   // buffers actually rotated through (<= kRing): fewer 
 static bool trunk_split() {
   static const bool v = [] { const char* e = getenv("SRES_TRUNK_SPLIT"); return e && atoi(e) != 0; }();
   return v;
+}
+// SRES_RCAB_CHAIN: 1 = a residual group's RCAB chain runs as ONE image-resident cluster launch (rcab_chain.cu) when the
+// geometry fits; 0 = per RCAB the fused pair launch + channel-attention kernel.  Read at every forward call (not cached)
+// so that a test can run both paths in one process.
+static bool rcab_chain_enabled() {
+  const char* e = getenv("SRES_RCAB_CHAIN");
+  return e ? atoi(e) != 0 : SRES_RCAB_CHAIN_DEFAULT != 0;
 }
 static bool join_per_segment() {
   static const bool v = [] { const char* e = getenv("SRES_JOIN_PER_SEG"); return e && atoi(e) != 0; }();
@@ -385,9 +395,28 @@ static int forward(const Net& n, const float* P, const float* x, float* out, uin
       ++xbi;
     }
   }
+  const bool chain = !n.edsr && rcab_chain_enabled() && fused_pool && sres_rcab_chain_supported(B, H, W);
   for (int g = 0; g < (n.edsr ? 0 : G); ++g) {
     float* gout = (float*)(ws + n.o_gf[g & 1]);
-    for (int r = 0; r < R; ++r) {
+    if (chain) {
+      PROF("rcab chain fwd (R blocks)");
+      sres_rcab_chain_args ca;
+      memset(&ca, 0, sizeof(ca));
+      ca.xb_bf16 = ws + n.o_xb; ca.t1_bf16 = ws + n.o_t1; ca.t2_bf16 = ws + n.o_t2;
+      ca.wpack_bf16 = WF(n.cidx(g, 0, 0));
+      ca.params = P + n.off_rcab(g, 0);
+      ca.x_in_f32 = gin; ca.x_f32 = xf;
+      ca.save_mean = (float*)(ws + n.o_mean) + (size_t)(training ? g * R : 0) * B * 64;
+      ca.save_s = (float*)(ws + n.o_s) + (size_t)(training ? g * R : 0) * B * 64;
+      ca.scratch = pool_part;   // per-tile partial sums are not used on this path: the buffer serves as the [B][2][64] scratch
+      ca.rcab_stride = n.rcab_sz; ca.save_stride = training ? (long long)B * 64 : 0;
+      ca.B = B; ca.H = H; ca.W = W; ca.n_blocks = R; ca.hidden = n.hid;
+      ca.xb_first = xbi; ca.xb_ring = training ? 0 : 2; ca.xb_count = n.n_xb;
+      ca.t_first = training ? g * R : 0; ca.t_fixed = training ? 0 : 1; ca.t_count = n.n_t;
+      RC(sres_rcab_chain_fwd(&ca, st));
+      xbi += R;
+    }
+    for (int r = 0; r < (chain ? 0 : R); ++r) {
       const int ti = g * R + r;
       const float* pr = P + n.off_rcab(g, r);
       const float* c1b = pr + kConvW;
