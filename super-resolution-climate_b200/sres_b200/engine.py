@@ -229,7 +229,16 @@ class RcanEngine:
         whole = self._bwd_count.get((key, 0, nseg))
         if whole is not None:
             return whole
-        return sum(self._bwd_count[(key, s, s + 1)] for s in range(nseg))
+        # the pass ran as several calls (data parallel: one per all-reduce bucket): chain the recorded ranges from segment 0
+        total, s = 0, 0
+        while s < nseg:
+            ends = [e for (k, b, e) in self._bwd_count if k == key and b == s]
+            if not ends:
+                raise L.SresError(f"launches_backward: no backward call starting at segment {s} has run yet")
+            e = max(ends)
+            total += self._bwd_count[(key, s, e)]
+            s = e
+        return total
 
     # -- forward / backward ---------------------------------------------------------------------
     def _launch_forward(self, key, x, out, ws, always_pack=False):

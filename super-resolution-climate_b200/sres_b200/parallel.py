@@ -1,5 +1,5 @@
 """Data parallelism over tile batches: one process per GPU, NCCL all-reduce of the flat gradient
-buffer, issued segment by segment on a side stream so it overlaps the rest of backward.
+buffer, issued bucket by bucket (groups of backward segments) on a side stream so it overlaps the rest of backward.
 
 Not in the reference (single process, single device: sres/base/gpu.py:6-15); SURVEY.md 8e.
 Tiles are independent units (no inter-tile halo, no BatchNorm), weights and optimizer state are
@@ -61,16 +61,46 @@ def gather_ranges(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor
 
 
 class SegmentAllReduce:
-    def __init__(self, engine, process_group=None, average: bool = False):
+    def __init__(self, engine, process_group=None, average: bool = False, n_buckets: Optional[int] = None):
         if not dist.is_initialized():
             raise RuntimeError("enable_data_parallel: torch.distributed is not initialised")
         self.group = process_group
         self.world = dist.get_world_size(process_group)
         self.average = average
+        if n_buckets is None:
+            import os
+            # Measured on 8 x B200 (profiles/r02_dp8_buckets.txt): one all-reduce per backward segment (12 NCCL launches whose
+            # CTAs displace the persistent tensor-core kernels' CTAs, and 12 graph replays) 28.65 ms per step; ONE bucket after
+            # the whole backward (65 MB, exposed) 27.95 ms; TWO buckets (the first overlaps the second half of backward)
+            # 27.81 ms against 27.07 ms on one GPU of the same box.
+            n_buckets = int(os.environ.get("SRES_DP_BUCKETS", "2"))
         self.on_gpu = torch.device(engine.device).type == "cuda"
         self.comm_stream = torch.cuda.Stream(device=engine.device) if self.on_gpu else None
         self.segments = [engine.segment_params(s) for s in range(engine.num_segments())]
+        self.buckets = self._make_buckets(self.segments, n_buckets)
         self.trace = None   # development aid (tools/dp_timeline.py): list of (label, stream name, event) when not None
+
+    @staticmethod
+    def _make_buckets(segments, n_buckets):
+        """Group consecutive backward segments into `n_buckets` all-reduce buckets of roughly equal parameter count.
+        Consecutive segments complete adjacent, descending parameter ranges (segment 0 = the end of the flat buffer), so a
+        group is one contiguous range: (seg_begin, seg_end, offset, count).  None / 0 = one bucket per segment."""
+        nseg = len(segments)
+        if not n_buckets or n_buckets >= nseg:
+            return [(s, s + 1, off, cnt) for s, (off, cnt) in enumerate(segments)]
+        total = sum(c for _, c in segments)
+        buckets, begin, acc = [], 0, 0
+        for s, (off, cnt) in enumerate(segments):
+            acc += cnt
+            left = n_buckets - len(buckets) - 1          # buckets still to open after this one
+            if s == nseg - 1 or (acc >= total * (len(buckets) + 1) / n_buckets and nseg - 1 - s >= left):
+                lo = min(o for o, _ in segments[begin:s + 1])
+                hi = max(o + c for o, c in segments[begin:s + 1])
+                if hi - lo != sum(c for _, c in segments[begin:s + 1]):
+                    raise RuntimeError("backward segments of one bucket do not form a contiguous parameter range")
+                buckets.append((begin, s + 1, lo, hi - lo))
+                begin = s + 1
+        return buckets
 
     def _mark(self, label, stream, name):
         if self.trace is not None and self.on_gpu:
@@ -91,8 +121,8 @@ class SegmentAllReduce:
             raise RuntimeError("data-parallel backward needs fresh gradients (optimizer.zero_grad() each step)")
         main = torch.cuda.current_stream(engine.device) if self.on_gpu else None
         self._mark("bwd begin", main, "main")
-        for seg, (off, cnt) in enumerate(self.segments):
-            engine.backward(xin, dout, accumulate=False, seg_begin=seg, seg_end=seg + 1)
+        for seg, seg_end, off, cnt in self.buckets:
+            engine.backward(xin, dout, accumulate=False, seg_begin=seg, seg_end=seg_end)
             if self.on_gpu:
                 ev = torch.cuda.Event()
                 ev.record(main)

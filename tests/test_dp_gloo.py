@@ -60,6 +60,13 @@ def _worker(rank, world, port, out_q):
         ok_sum = bool(torch.equal(eng.flat_grad, expect)) and eng.calls == list(range(eng.nseg)) and eng.launches == 7
         with pytest.raises(RuntimeError):
             ddp.backward(eng, None, None, accumulate=True)
+        # fewer, larger all-reduce buckets (SRES_DP_BUCKETS): consecutive segments merge into contiguous ranges, same sums
+        for nb in (1, 2, 3):
+            eng_b = _StubEngine(rank)
+            ddp_b = SegmentAllReduce(eng_b, None, average=False, n_buckets=nb)
+            ddp_b.backward(eng_b, None, None, accumulate=False)
+            ok_sum = ok_sum and len(ddp_b.buckets) == nb and bool(torch.equal(eng_b.flat_grad, expect)) and eng_b.calls == list(range(eng_b.nseg))
+            ok_sum = ok_sum and sum(c for _, _, _, c in ddp_b.buckets) == eng_b.n and ddp_b.buckets[0][0] == 0 and ddp_b.buckets[-1][1] == eng_b.nseg
         # global-batch RMSE: sqrt(sum_r SSE_r / (world * n_local)) == RMSE of the concatenated batch
         g = torch.Generator().manual_seed(1234)
         full = torch.randn(world * 6, 3, generator=g, dtype=torch.float64)
