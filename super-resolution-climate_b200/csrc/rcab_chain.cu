@@ -33,7 +33,7 @@ constexpr int kCAcc = 4;
 constexpr int kCStages = 4;
 constexpr int kCWBytes = 9 * 64 * 128;
 constexpr int kCConvW = 64 * 64 * 9;
-constexpr int kCTail = 3072;
+constexpr int kCTail = 3072;   // barriers (<= 512 B), biases, pooled sums, MLP vectors
 
 struct ChainParams {
   int B, H, W, P, RP, T;       // image geometry; T = M tiles per image
@@ -593,6 +593,346 @@ rcab_chain_fwd_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_con
   if (warp == 2) tmem_dealloc(tmem_base, kCAcc * 64);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Overlapped variant (SRES_CHAIN_OVERLAP=1): the streaming phase of block r runs UNDER conv1 of block r + 1.
+//
+// The plain kernel above spends 39 000 of its 100 000 cycles per block in x += T2 * s with the tensor core idle, and that
+// phase cannot go faster by itself: it moves 0.92 MB per CTA at 24 B/clk, the rate one SM gets out of L2 for a mixed
+// read / write stream (ncu: DRAM 26 %, L2 21 % of peak over the whole kernel -- nothing chip-wide is saturated).  But conv1 of
+// the next block needs, for its tile j, only the updated rows of tiles j-1, j, j+1.  So six extra "stream" warps (512 threads
+// per CTA) walk the CTA's tiles in a fixed order and publish each finished tile on a shared-memory mbarrier; the TMA producer
+// of conv1 waits for tile j+1's barrier before it loads the halo window of tile j.  The two CTAs of a cluster walk their
+// tiles AWAY from the boundary between them (rank 0 downwards, rank 1 upwards), so the one tile each needs from the other
+// is the first one finished; it is published with a remote arrive on the partner's barrier.  Per block there remain two
+// cluster barriers: after conv1 (T1 complete) and in the pooled-mean exchange.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kOThreads = 512;
+constexpr int kOStream = 6;        // stream warps: 2, 3, 12, 13, 14, 15
+constexpr int kOMaxTiles = 16;     // tiles per CTA (one publication barrier each)
+
+__global__ void __launch_bounds__(kOThreads, 1)
+rcab_chain_ovl_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_constant__ CUtensorMap tmT1s,
+                      const __grid_constant__ CUtensorMap tmT1a, const __grid_constant__ CUtensorMap tmT2s,
+                      const __grid_constant__ CUtensorMap tmW, const ChainParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_a = smem + p.off_ring;
+  const int stage_bytes = p.stage_rows * 128;
+  uint8_t* tail = smem + p.off_tail;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(tail);   // [kCStages]
+  uint64_t* bar_empty = bar_full + kCStages;                // [kCStages]
+  uint64_t* bar_w = bar_empty + kCStages;                   // [2]
+  uint64_t* bar_tfull = bar_w + 2;                          // [kCAcc]
+  uint64_t* bar_tempty = bar_tfull + kCAcc;                 // [kCAcc]
+  uint64_t* bar_xb = bar_tempty + kCAcc;                    // [kOMaxTiles] tile (in walking order) updated by the stream warps
+  uint64_t* bar_nbr = bar_xb + kOMaxTiles;                  // [1] the partner CTA's boundary tile updated (remote arrives)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_nbr + 1);
+  float* s_bias = reinterpret_cast<float*>(tail + 512);     // [2][64]
+  float* s_pool = s_bias + 128;                             // [4][64]
+  float* sm_m = s_pool + 256;
+  float* sm_h = sm_m + 64;
+  float* sm_s = sm_h + 64;
+
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int lane = tid & 31;
+  const int k = p.K > 1 ? (int)cluster_ctarank() : 0;
+  const int b = blockIdx.x / p.K;
+  const int j0 = k * p.tpc;
+  const int j1 = min(p.T, j0 + p.tpc);
+  const int n_my = max(0, j1 - j0);
+  const bool down = p.K > 1 && k == 0;                      // rank 0 walks its tiles downwards, away from the boundary
+  auto tile_of = [&](int jj) { return down ? j1 - 1 - jj : j0 + jj; };
+  long long* tl = p.timeline ? p.timeline + (size_t)blockIdx.x * 16 : nullptr;   // bring-up: cycles summed over the blocks
+  if (tl && tid == 0) { tl[0] = clock64(); for (int i = 1; i < 16; ++i) tl[i] = 0; }
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmXa);
+    tma_prefetch_desc(&tmT1s);
+    tma_prefetch_desc(&tmT1a);
+    tma_prefetch_desc(&tmT2s);
+    tma_prefetch_desc(&tmW);
+    for (int i = 0; i < kCStages; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    mbar_init(&bar_w[0], 1);
+    mbar_init(&bar_w[1], 1);
+    for (int i = 0; i < kCAcc; ++i) {
+      mbar_init(&bar_tfull[i], 1);
+      mbar_init(&bar_tempty[i], 8);
+    }
+    for (int i = 0; i < kOMaxTiles; ++i) mbar_init(&bar_xb[i], kOStream);
+    mbar_init(bar_nbr, kOStream);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_holder, kCAcc * 64);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (p.K > 1) cluster_sync_all();   // the partner's barriers exist before anyone arrives on them remotely
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
+  pdl_launch_dependents();
+
+  const bool leader = (warp == 0 || warp == 1) ? elect_one() : false;
+  if (warp == 0 && n_my > 0 && leader) {
+    for (int c = 0; c < 2; ++c) {
+      mbar_expect_tx(&bar_w[c], kCWBytes);
+      for (int t = 0; t < 9; ++t) tma_load_2d((smem + c * kCWBytes) + t * 64 * 128, &tmW, &bar_w[c], 0, c * 576 + t * 64);
+    }
+  }
+  __syncwarp();
+  pdl_wait();
+
+  int it = 0;
+  const uint32_t row_step = uint32_t(p.P) * 8;
+  const int wq = warp & 3, ew = warp - 4, half = (ew >> 2) & 1;
+  const bool is_epi = warp >= 4 && warp < 12;
+  const bool is_stream = warp == 2 || warp == 3 || warp >= 12;
+  uint8_t* s16 = smem + p.off_s16 + (is_epi ? ew : 0) * 2048;
+  const int fm = lane & 3;
+  auto xb_idx = [&](int r) { return p.xb_ring ? (p.xb_first + r) % p.xb_ring : p.xb_first + r; };
+  auto t_idx = [&](int r) { return p.t_fixed ? p.t_first : p.t_first + r; };
+
+  // one convolution (c = 0: conv1, 1: conv2) of block rb by the producer / MMA / epilogue warps; `gate`: the producer waits
+  // for the stream warps' publication of block rb - 1's update before each halo window
+  auto conv_phase = [&](const int c, const int rb, const bool gate) {
+    const int tb = t_idx(rb);
+    if (warp == 0) {
+      if (leader) fence_proxy_async_all();
+      const uint32_t xpar = uint32_t(rb - 1) & 1u;
+      for (int jj = 0; jj < n_my; ++jj, ++it) {
+        const int slot = it % p.nstage;
+        const uint32_t ph = (it / p.nstage) & 1;
+        if (gate) {
+          long long g0 = 0;
+          if (tl) g0 = clock64();
+          mbar_wait(&bar_xb[min(jj + 1, n_my - 1)], xpar, 9);
+          if (jj == 0 && p.K > 1) mbar_wait(bar_nbr, xpar, 10);
+          if (tl && lane == 0) tl[5] += clock64() - g0;   // producer waiting for the stream warps (own tiles + partner's boundary tile)
+          if (leader) fence_proxy_async_all();   // the stream warps' generic stores -> this TMA load
+        }
+        mbar_wait(&bar_empty[slot], ph ^ 1, 1);
+        const int row0 = tile_of(jj) * 128 - (p.P + 1);
+        uint8_t* dst = smem_a + slot * stage_bytes;
+        if (leader) {
+          mbar_expect_tx(&bar_full[slot], stage_bytes);
+          for (int rr = 0; rr < p.stage_rows; rr += p.box_rows)
+            tma_load_4d(dst + rr * 128, c == 0 ? &tmXa : &tmT1a, &bar_full[slot], 0, row0 + rr, b, c == 0 ? xb_idx(rb) : tb);
+        }
+        __syncwarp();
+      }
+      if (rb + 1 < p.n_blocks && n_my > 0) {   // the next block's weights of this convolution, once this phase's MMAs have retired
+        const int last = it - 1;
+        mbar_wait(&bar_empty[last % p.nstage], (last / p.nstage) & 1, 7);
+        if (leader) {
+          mbar_expect_tx(&bar_w[c], kCWBytes);
+          for (int t = 0; t < 9; ++t)
+            tma_load_2d((smem + c * kCWBytes) + t * 64 * 128, &tmW, &bar_w[c], 0, (2 * (rb + 1) + c) * 576 + t * 64);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1) {
+      if (n_my > 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+        constexpr uint32_t dhi = sdesc_hi_sw128(1024);
+        mbar_wait(&bar_w[c], rb & 1, 2);
+        tc_fence_after();
+        const uint32_t w_lo = sdesc_lo(smem_u32(smem + c * kCWBytes), 16);
+        const uint32_t a_lo0 = sdesc_lo(smem_u32(smem_a), 16);
+        for (int jj = 0; jj < n_my; ++jj, ++it) {
+          const int slot = it % p.nstage;
+          const uint32_t ph = (it / p.nstage) & 1;
+          const int acc = it % kCAcc;
+          const uint32_t aph = (it / kCAcc) & 1;
+          mbar_wait(&bar_tempty[acc], aph ^ 1, 3);
+          mbar_wait(&bar_full[slot], ph, 4);
+          tc_fence_after();
+          const uint32_t a_tile = a_lo0 + uint32_t(slot * stage_bytes) / 16;
+          const uint32_t d_tmem = tmem_base + uint32_t(acc * 64);
+          if (leader) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const uint32_t a_tap = a_tile + uint32_t(t / 3) * row_step + uint32_t(t % 3) * 8;
+              const uint32_t b_tap = w_lo + uint32_t(t * 64 * 8);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                if (t == 0 && kk == 0) umma_bf16_lohi<false>(d_tmem, a_tap, dhi, b_tap, dhi, idesc);
+                else umma_bf16_lohi<true>(d_tmem, a_tap + kk * 2, dhi, b_tap + kk * 2, dhi, idesc);
+              }
+            }
+            umma_commit(&bar_empty[slot]);
+            umma_commit(&bar_tfull[acc]);
+          }
+          __syncwarp();
+        }
+      }
+    } else if (is_epi) {
+      float bias8[8], cs[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        bias8[i] = s_bias[64 + half * 32 + 8 * (i >> 1) + 2 * fm + (i & 1)];
+        cs[i] = 0.f;
+      }
+      for (int jj = 0; jj < n_my; ++jj, ++it) {
+        const int acc = it % kCAcc;
+        const uint32_t aph = (it / kCAcc) & 1;
+        const int r_img0 = tile_of(jj) * 128 + wq * 32;
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+        mbar_wait(&bar_tfull[acc], aph, 5);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + (uint32_t(wq * 32) << 16) + uint32_t(acc * 64 + half * 32);
+        if (c == 0) chain_epi_rows(p, s_bias, s16, r_img0 + lane, half, lane, trow);
+        else chain_epi_frag(p, bias8, cs, s16, r_img0, lane, trow);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(c == 0 ? &tmT1s : &tmT2s, s16, half * 32, r_img0, b, tb);
+          bulk_commit();
+        }
+      }
+      if (lane == 0) bulk_wait_all<0>();
+      __syncwarp();
+      if (c == 1) {
+        const float tot = frag_colsum(cs, lane);
+        const int fcol = ((lane >> 4) & 1) * 16 + ((lane >> 3) & 1) * 8 + 2 * fm + ((lane >> 2) & 1);
+        s_pool[wq * 64 + half * 32 + fcol] = tot;
+      }
+    }
+  };
+  auto barrier_all = [&]() { if (p.K > 1) cluster_sync_all(); else __syncthreads(); };
+
+  {
+    const float* prm = p.params;
+    if (tid < 64) s_bias[tid] = prm[kCConvW + tid];
+    else if (tid < 128) s_bias[tid] = prm[2 * kCConvW + 64 + (tid - 64)];
+  }
+  __syncthreads();
+  conv_phase(0, 0, false);
+  barrier_all();   // T1 of block 0 complete
+
+#pragma unroll 1
+  for (int r = 0; r < p.n_blocks; ++r) {
+    const float* prm = p.params + (long long)r * p.rcab_stride;
+    long long c0 = 0;
+    if (tl) c0 = clock64();
+    conv_phase(1, r, false);
+    if (tl && tid == 128) tl[1] += clock64() - c0;      // conv2 phase (epilogue thread)
+    // ---- pooled mean -> gate ----
+    __syncthreads();
+    if (tid < 64) {
+      const float sum = (s_pool[tid] + s_pool[64 + tid]) + (s_pool[128 + tid] + s_pool[192 + tid]);
+      __stcg(p.pool_scratch + ((size_t)b * p.K + k) * 64 + tid, n_my > 0 ? sum : 0.f);
+      __threadfence();
+    }
+    barrier_all();
+    const float* w1 = prm + 2 * (kCConvW + 64);
+    const float* b1 = w1 + p.hid * 64;
+    const float* w2 = b1 + p.hid;
+    const float* b2 = w2 + 64 * p.hid;
+    if (tid < 64) {
+      float tot = 0.f;
+      for (int kk = 0; kk < p.K; ++kk) tot += __ldcg(p.pool_scratch + ((size_t)b * p.K + kk) * 64 + tid);
+      sm_m[tid] = tot / float(p.H * p.W);
+    }
+    if (r + 1 < p.n_blocks) {   // biases of the next block (this block's epilogues are done with theirs)
+      const float* pn = prm + p.rcab_stride;
+      if (tid >= 128 && tid < 192) s_bias[tid - 128] = pn[kCConvW + (tid - 128)];
+      else if (tid >= 192 && tid < 256) s_bias[64 + tid - 192] = pn[2 * kCConvW + 64 + (tid - 192)];
+    }
+    __syncthreads();
+    {
+      const float m0 = sm_m[lane], m1 = sm_m[lane + 32];
+      for (int j = warp; j < p.hid; j += kOThreads / 32) {
+        const float v = chain_warp_sum(fmaf(__ldg(w1 + j * 64 + lane), m0, __ldg(w1 + j * 64 + 32 + lane) * m1));
+        if (lane == 0) sm_h[j] = fmaxf(v + __ldg(b1 + j), 0.f);
+      }
+    }
+    __syncthreads();
+    if (tid < 64) {
+      float z = __ldg(b2 + tid);
+      for (int j = 0; j < p.hid; ++j) z = fmaf(__ldg(w2 + tid * p.hid + j), sm_h[j], z);
+      const float sg = 1.f / (1.f + expf(-z));
+      sm_s[tid] = sg;
+      if (k == 0) {
+        p.save_mean[(long long)r * p.save_stride + b * 64 + tid] = sm_m[tid];
+        p.save_s[(long long)r * p.save_stride + b * 64 + tid] = sg;
+      }
+    }
+    __syncthreads();
+
+    // ---- x <- x + T2 * s by the stream warps, tile by tile, under conv1 of the next block ----
+    long long b0 = 0;
+    if (tl) { b0 = clock64(); if (tid == 128) tl[2] += b0 - c0; }   // conv2 + pool exchange + MLP
+    if (is_stream) {
+      const int sidx = warp < 4 ? warp - 2 : warp - 10;
+      const int lr = sidx * 4 + (lane >> 3), cg = lane & 7;
+      float s8[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s8[j] = sm_s[cg * 4 + j]; s8[4 + j] = sm_s[32 + cg * 4 + j]; }
+      const float* xin = r == 0 ? p.x_in : p.xf;
+      const uint16_t* t2 = p.t2_base + (long long)t_idx(r) * p.buf_stride;
+      uint16_t* xbo = p.xb_base + (long long)xb_idx(r + 1) * p.buf_stride;
+      constexpr int kU = 6, kStep = kOStream * 4;   // 6 x 24 rows >= one 128-row tile: every load of a tile is in flight at once
+      for (int jj = 0; jj < n_my; ++jj) {
+        const int rbase = tile_of(jj) * 128, rend = min(p.RP, rbase + 128);
+        uint2 ta[kU], tc[kU];
+        float4 xa[kU], xc[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int rr = min(rbase + lr + u * kStep, rend - 1);
+          const size_t q = (size_t)b * p.RP + rr;
+          ta[u] = __ldcg(reinterpret_cast<const uint2*>(t2 + q * 64 + cg * 4));
+          tc[u] = __ldcg(reinterpret_cast<const uint2*>(t2 + q * 64 + 32 + cg * 4));
+          xa[u] = __ldcg(reinterpret_cast<const float4*>(xin + q * 64 + cg * 4));
+          xc[u] = __ldcg(reinterpret_cast<const float4*>(xin + q * 64 + 32 + cg * 4));
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int rr = rbase + lr + u * kStep;
+          if (rr < rend) {
+            const size_t q = (size_t)b * p.RP + rr;
+            float o[8];
+            o[0] = fmaf(bf16_lo(ta[u].x), s8[0], xa[u].x); o[1] = fmaf(bf16_hi(ta[u].x), s8[1], xa[u].y);
+            o[2] = fmaf(bf16_lo(ta[u].y), s8[2], xa[u].z); o[3] = fmaf(bf16_hi(ta[u].y), s8[3], xa[u].w);
+            o[4] = fmaf(bf16_lo(tc[u].x), s8[4], xc[u].x); o[5] = fmaf(bf16_hi(tc[u].x), s8[5], xc[u].y);
+            o[6] = fmaf(bf16_lo(tc[u].y), s8[6], xc[u].z); o[7] = fmaf(bf16_hi(tc[u].y), s8[7], xc[u].w);
+            __stcg(reinterpret_cast<float4*>(p.xf + q * 64 + cg * 4), make_float4(o[0], o[1], o[2], o[3]));
+            __stcg(reinterpret_cast<float4*>(p.xf + q * 64 + 32 + cg * 4), make_float4(o[4], o[5], o[6], o[7]));
+            __stcg(reinterpret_cast<uint2*>(xbo + q * 64 + cg * 4), make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3])));
+            __stcg(reinterpret_cast<uint2*>(xbo + q * 64 + 32 + cg * 4), make_uint2(pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7])));
+          }
+        }
+        __threadfence();              // this thread's rows are visible gpu-wide ...
+        fence_proxy_async_all();      // ... also to the async proxy (TMA loads of this CTA and of the partner)
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&bar_xb[jj]);
+          if (jj == 0 && p.K > 1) mbar_arrive_cluster(mapa_u32(smem_u32(bar_nbr), uint32_t(k ^ 1)));
+        }
+      }
+      if (tl && warp == 2 && lane == 0) tl[3] += clock64() - b0;   // streaming of this block (stream warp 2)
+    } else if (r + 1 < p.n_blocks) {
+      conv_phase(0, r + 1, true);
+      if (tl && tid == 128) tl[4] += clock64() - b0;               // gated conv1 of the next block (epilogue thread)
+    }
+    barrier_all();   // T1 of block r + 1 complete, block r's update complete everywhere
+    if (tl && tid == 128) tl[6] += clock64() - b0;                 // whole overlapped phase incl. the barrier
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (tl && tid == 0) tl[9] = clock64();
+  if (warp == 2) tmem_dealloc(tmem_base, kCAcc * 64);
+}
+
 // shared-memory plan; false when two weight regions leave no room for a two-slot halo ring
 static bool chain_plan(int H, int W, ChainParams* p, size_t* smem_bytes) {
   const int smem_max = 232448;
@@ -732,6 +1072,15 @@ extern "C" int sres_rcab_chain_fwd(const sres_rcab_chain_args* a, void* stream_)
     if (e2 != cudaSuccess) return e2;
     return cudaLaunchKernelEx(&cfg, kern, tmXa, tmT1s, tmT1a, tmT2s, tmW, p);
   };
+  static const int ovl_env = [] { const char* e = getenv("SRES_CHAIN_OVERLAP"); return e ? atoi(e) : 0; }();
+  if (ovl_env && p.tpc <= kOMaxTiles) {
+    cfg.blockDim = dim3(kOThreads);
+    e = launch(rcab_chain_ovl_kernel);
+    if (e != cudaSuccess) return set_cuda_error(e, "rcab_chain: launch (overlapped)");
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, "rcab_chain: launch (overlapped)");
+    return SRES_OK;
+  }
   const bool dbg = p.timeline != nullptr, lend = p.lend != 0, bulk = p.ap_nbuf >= 3;
   if (dbg) e = lend ? (bulk ? launch(rcab_chain_fwd_kernel<true, true, true>) : launch(rcab_chain_fwd_kernel<true, false, true>))
                     : (bulk ? launch(rcab_chain_fwd_kernel<false, true, true>) : launch(rcab_chain_fwd_kernel<false, false, true>));

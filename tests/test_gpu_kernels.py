@@ -622,6 +622,25 @@ def test_rcab_chain_equals_kernel_by_kernel(env, B, H, W, nb, red, training):
     assert torch.equal(xf_d, xf_c) and torch.equal(s_d, s_c) and torch.equal(t2_d.view(torch.int16), t2_c.view(torch.int16))
 
 
+@pytest.mark.parametrize("setting", ["SRES_CHAIN_OVERLAP=1", "SRES_CHAIN_LEND=1", "SRES_CHAIN_BULK=1", "SRES_CHAIN_K=1", "SRES_CHAIN_LEND=1 SRES_CHAIN_BULK=1"])
+def test_rcab_chain_variants_keep_parity(setting):
+    """The chain kernel's measured variants (streaming under the next conv1 with six extra warps, 4-deep halo ring through the
+    idle weight region, bulk-copy streaming phase, one CTA per image) are selected by environment switches that the library
+    reads once per process: the same kernel-by-kernel parity test runs in a fresh interpreter for each of them."""
+    import os
+    import subprocess
+    import sys
+    env_ = dict(os.environ)
+    for kv in setting.split():
+        key, val = kv.split("=")
+        env_[key] = val
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_kernels.py"), "-q", "-x", "-m", "gpu", "-k",
+                        "test_rcab_chain_equals_kernel_by_kernel", "-p", "no:cacheprovider"], env=env_, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "5 passed" in r.stdout, r.stdout[-1000:]
+
+
 def test_bicubic_matches_interpolate(env):
     L, lib, dev = env
     from sres_b200 import nn as snn

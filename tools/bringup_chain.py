@@ -58,6 +58,15 @@ a.debug_timeline = tl.data_ptr()
 for _ in range(2):
     L.check(lib.sres_rcab_chain_fwd(C.byref(a), st), "chain"); torch.cuda.synchronize()
 t = tl.cpu().double()
+if os.environ.get("SRES_CHAIN_OVERLAP", "0") != "0":
+    print(f"cycles per CTA over the launch: median {(t[:, 9] - t[:, 0]).median():.0f}; per RCAB {(t[:, 9] - t[:, 0]).median() / nb:.0f}")
+    for rk in (0, 1):
+        sel = t[rk::2]
+        print(f" cluster rank {rk}: cycles per RCAB, median over CTAs")
+        for i, n in ((1, "conv2 phase"), (2, "conv2 + pool exchange + MLP"), (3, "streaming x += t2*s (stream warp 2)"), (4, "gated conv1 of the next block"),
+                     (5, "producer waiting for the stream warps"), (6, "whole overlapped phase incl. barrier")):
+            print(f"   {n:40s} {sel[:, i].median() / nb:9.0f}")
+    sys.exit(0)
 names = ["conv1 phase (epilogue thread)", "S1 wait (T1 stored, cluster)", "conv2 phase", "pool exchange + S2", "gate MLP", "apply x += t2*s", "S3 wait"]
 tot = (t[:, 9] - t[:, 0])
 print(f"cycles per CTA over the launch: median {tot.median():.0f} (min {tot.min():.0f}, max {tot.max():.0f}); per RCAB {tot.median() / nb:.0f}")
