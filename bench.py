@@ -367,13 +367,16 @@ def run_cuda(args):
     ms_total = float(t.item())
     value = world * B * args.steps / (ms_total / 1e3)
 
-    # ---- e2e: host buffers through the public trainer-style call, H2D + loss D2H inside the timed region
-    for i in range(2):
-        step(host[i % nbuf]).item()      # pinned host batch in, python float out
+    # ---- e2e: host buffers through the public trainer-style call, H2D + loss D2H inside the timed region.
+    # ModelTrainer.train_stream takes pinned HOST batches and yields one loss per optimizer step; it issues batch i+1's
+    # host-to-device copy on a copy stream before it enqueues step i, so every step's copy is inside the timed region but
+    # runs under the previous step's kernels; each loss is read back to a python float before the next step is enqueued.
+    for lossv in trainer.train_stream(host[i % nbuf] for i in range(2)):
+        lossv.item()
     sync_all()
     e0.record()
-    for i in range(args.steps):
-        step(host[i % nbuf]).item()
+    for lossv in trainer.train_stream(host[i % nbuf] for i in range(args.steps)):
+        lossv.item()                     # pinned host batch in, python float out
     e1.record()
     sync_all()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)

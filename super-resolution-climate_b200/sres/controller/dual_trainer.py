@@ -164,6 +164,41 @@ class ModelTrainer(object):
         self.optimizer.step()
         return mloss.detach()
 
+    def train_stream(self, host_batches):
+        """Optimizer steps over an iterable of HOST batches (pinned memory for a truly asynchronous copy): the host-to-device
+        copy of batch i+1 is issued on a copy stream before step i is enqueued, so it runs under step i's kernels instead of
+        in front of step i+1's.  Yields each step's loss as a device scalar (reading it with .item() does not wait for the
+        next batch's copy).  Same arithmetic as calling train_step batch by batch."""
+        dev = self.device
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+
+        def stage(hb):
+            data = hb.data if isinstance(hb, TileArray) else hb
+            if not isinstance(data, torch.Tensor):
+                data = torch.from_numpy(np.ascontiguousarray(data))
+            with torch.cuda.stream(self._copy_stream):
+                d = data.to(device=dev, dtype=torch.float32, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            d.record_stream(main)          # allocated on the copy stream, consumed on the compute stream
+            return d, ev
+
+        it = iter(host_batches)
+        try:
+            nxt = stage(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur, ev = nxt
+            try:
+                nxt = stage(next(it))
+            except StopIteration:
+                nxt = None
+            main.wait_event(ev)
+            yield self.train_step(cur)
+
     # -- training loop -----------------------------------------------------------------------------
     def train(self, nepochs: int, refresh_state: bool, **kwargs) -> Dict[str, float]:
         if nepochs == 0:

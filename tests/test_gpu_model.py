@@ -688,6 +688,41 @@ def test_controller_api_train_and_infer(dev, tmp_path):
         ConfigContext.deactivate()
 
 
+def test_train_stream_equals_step_by_step(dev, tmp_path):
+    """ModelTrainer.train_stream (host batches in, the next batch's copy issued under the running step) walks exactly the
+    same optimizer steps as train_step batch by batch: identical losses and identical weights afterwards."""
+    from sres.base.util.config import ConfigContext
+    from sres.controller.workflow import WorkflowController
+    ConfigContext.deactivate()
+    over = {"model.nlayers": 2, "model.nblocks": 2, "task.batch_size": 6, "task.lr": 3e-4, "task.tile_size": dict(x=12, y=12),
+            "dataset.region": dict(ys=480, xs=480), "dataset.ntimes": 2, "platform.results": str(tmp_path)}
+    host = [synth_hr(6, 2, 48, seed=20 + i).pin_memory() for i in range(5)]
+    try:
+        out = []
+        for mode in range(2):
+            random.seed(3)
+            wc = WorkflowController("sres", dict(task="SSS_SST-tiles-48", dataset="synthetic_1200", platform="local"), seed=1)
+            wc.initialize("sres", "rcan-10-20-64", **over)
+            tr = wc.trainer
+            tr.model.train()
+            if mode == 0:
+                w0 = tr.model.engine.flat.detach().clone()
+            else:                      # same initial weights as the first trainer (each draws its own from torch's RNG)
+                tr.model.engine.flat.copy_(w0)
+                tr.model.engine.mark_params_changed()
+            if mode == 0:
+                losses = [tr.train_step(h.to(dev)).item() for h in host]
+            else:
+                losses = [l.item() for l in tr.train_stream(iter(host))]
+                assert list(tr.train_stream(iter([]))) == []
+            out.append((losses, tr.model.engine.flat.detach().clone()))
+            ConfigContext.deactivate()
+        assert out[0][0] == out[1][0] and all(np.isfinite(out[0][0]))
+        assert torch.equal(out[0][1], out[1][1])
+    finally:
+        ConfigContext.deactivate()
+
+
 def test_edsr_through_the_controller_and_segments(dev, tmp_path):
     """EDSR through the mirrored factory / trainer: `model: edsr` picks sres.model.edsr.network,
     state_dict keys are the reference's, training runs and checkpoints, backward splits into 3 DP segments."""
