@@ -10,4 +10,4 @@ python bench.py --steps 2 --warmup 3 --no-cpu-baseline --skip-extras > gpurun_ou
 SRES_CUDA_GRAPHS=0 ncu --metrics gpu__time_duration.sum --clock-control none -s 4800 -c 2994 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --skip-extras > gpurun_out/ncu.log 2>&1
 tail -n 1 gpurun_out/plain.log | cut -c1-200; tail -n 3 gpurun_out/ncu.log | cut -c1-300; wc -l gpurun_out/launches.csv
-python tools/summarize_launches.py gpurun_out/launches.csv > gpurun_out/r02_v2_launches.md; head -34 gpurun_out/r02_v2_launches.md
+python tools/summarize_launches.py gpurun_out/launches.csv > gpurun_out/r02_v4_launches.md; head -34 gpurun_out/r02_v4_launches.md
