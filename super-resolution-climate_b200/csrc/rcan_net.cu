@@ -478,7 +478,7 @@ static int forward(const Net& n, const float* P, const float* x, float* out, uin
 // backward.  Segments: 0 = tail conv, upsampler, body-tail conv; 1..G = residual groups G-1..0;
 // G+1 = head conv.  A caller overlapping the gradient all-reduce runs them one at a time.
 // ---------------------------------------------------------------------------------------------
-// Deferred weight-gradient jobs: up to 4 of the same geometry go out as one batched launch.  A job only
+// Deferred weight-gradient jobs: up to SRES_WGRAD_BATCH (8) of the same geometry go out as one batched launch.  A job only
 // reads saved activations and a bf16 output-gradient buffer; the queue is flushed before any kernel that
 // overwrites such a buffer is enqueued, when it is full, and at the end of every backward segment.
 // Optional second stream for the weight-gradient batches: they depend only on saved activations and on

@@ -67,6 +67,17 @@ def test_param_count_and_segments(lib):
         off, cnt = C.c_int64(), C.c_int64()
         assert lib.sres_rcan_segment_params(C.byref(d), s, C.byref(off), C.byref(cnt)) == 0
         spans.append((off.value, cnt.value))
+    # the data-parallel all-reduce buckets (groups of consecutive segments) are contiguous parameter ranges, cover the buffer
+    # once and are balanced: two buckets of RCAN-full split after the fifth residual group from the end
+    from sres_b200.parallel import SegmentAllReduce
+    for nb in (0, 1, 2, 3, 4, 12, 40):
+        buckets = SegmentAllReduce._make_buckets(spans, nb)
+        assert len(buckets) == (nseg if nb == 0 or nb >= nseg else nb)
+        assert [b[0] for b in buckets] == [0] + [b[1] for b in buckets[:-1]] and buckets[-1][1] == nseg
+        cover = sorted((off, cnt) for _, _, off, cnt in buckets)
+        assert cover[0][0] == 0 and all(a[0] + a[1] == b[0] for a, b in zip(cover, cover[1:])) and cover[-1][0] + cover[-1][1] == n
+    two = SegmentAllReduce._make_buckets(spans, 2)
+    assert (two[0][0], two[0][1], two[1][1]) == (0, 6, 12) and abs(two[0][3] - two[1][3]) < 0.1 * n
     spans.sort()
     assert spans[0][0] == 0 and all(a[0] + a[1] == b[0] for a, b in zip(spans, spans[1:])) and spans[-1][0] + spans[-1][1] == n
     ws = C.c_size_t()
