@@ -881,10 +881,10 @@ rcab_chain_ovl_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_con
       const uint16_t* t2 = p.t2_base + (long long)t_idx(r) * p.buf_stride;
       uint16_t* xbo = p.xb_base + (long long)xb_idx(r + 1) * p.buf_stride;
       constexpr int kU = 6, kStep = kOStream * 4;   // 6 x 24 rows >= one 128-row tile: every load of a tile is in flight at once
-      for (int jj = 0; jj < n_my; ++jj) {
+      uint2 ta[kU], tc[kU];
+      float4 xa[kU], xc[kU];
+      auto issue_loads = [&](int jj) {
         const int rbase = tile_of(jj) * 128, rend = min(p.RP, rbase + 128);
-        uint2 ta[kU], tc[kU];
-        float4 xa[kU], xc[kU];
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
           const int rr = min(rbase + lr + u * kStep, rend - 1);
@@ -894,6 +894,10 @@ rcab_chain_ovl_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_con
           xa[u] = __ldcg(reinterpret_cast<const float4*>(xin + q * 64 + cg * 4));
           xc[u] = __ldcg(reinterpret_cast<const float4*>(xin + q * 64 + 32 + cg * 4));
         }
+      };
+      if (n_my > 0) issue_loads(0);
+      for (int jj = 0; jj < n_my; ++jj) {
+        const int rbase = tile_of(jj) * 128, rend = min(p.RP, rbase + 128);
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
           const int rr = rbase + lr + u * kStep;
@@ -910,6 +914,9 @@ rcab_chain_ovl_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_con
             __stcg(reinterpret_cast<uint2*>(xbo + q * 64 + 32 + cg * 4), make_uint2(pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7])));
           }
         }
+        // the next tile's loads go out BEFORE this tile's stores are fenced: the two latencies overlap (issued after the
+        // fence, a tile cost load latency + store / fence latency = 5 900 cycles and the six warps needed 59 000 per block)
+        if (jj + 1 < n_my) issue_loads(jj + 1);
         __threadfence();              // this thread's rows are visible gpu-wide ...
         fence_proxy_async_all();      // ... also to the async proxy (TMA loads of this CTA and of the partner)
         __syncwarp();
