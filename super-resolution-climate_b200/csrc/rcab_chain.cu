@@ -605,6 +605,8 @@ rcab_chain_fwd_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_con
 // tiles AWAY from the boundary between them (rank 0 downwards, rank 1 upwards), so the one tile each needs from the other
 // is the first one finished; it is published with a remote arrive on the partner's barrier.  Per block there remain two
 // cluster barriers: after conv1 (T1 complete) and in the pooled-mean exchange.
+// Measured: correct, and slower than the plain kernel -- six warps stream 0.92 MB in 54 000 cycles where twelve
+// need 39 000, and the gated conv1 trails them; kept as a parity-tested opt-in.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kOThreads = 512;
 constexpr int kOStream = 6;        // stream warps: 2, 3, 12, 13, 14, 15
@@ -662,8 +664,8 @@ rcab_chain_ovl_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_con
       mbar_init(&bar_tfull[i], 1);
       mbar_init(&bar_tempty[i], 8);
     }
-    for (int i = 0; i < kOMaxTiles; ++i) mbar_init(&bar_xb[i], kOStream);
-    mbar_init(bar_nbr, kOStream);
+    for (int i = 0; i < kOMaxTiles; ++i) mbar_init(&bar_xb[i], kOStream / 2);   // one group of three stream warps per tile
+    mbar_init(bar_nbr, kOStream / 2);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -710,6 +712,7 @@ rcab_chain_ovl_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_con
         if (gate) {
           long long g0 = 0;
           if (tl) g0 = clock64();
+          mbar_wait(&bar_xb[jj], xpar, 9);                        // (tile jj - 1 was waited for one iteration ago)
           mbar_wait(&bar_xb[min(jj + 1, n_my - 1)], xpar, 9);
           if (jj == 0 && p.K > 1) mbar_wait(bar_nbr, xpar, 10);
           if (tl && lane == 0) tl[5] += clock64() - g0;   // producer waiting for the stream warps (own tiles + partner's boundary tile)
@@ -872,22 +875,26 @@ rcab_chain_ovl_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_con
     long long b0 = 0;
     if (tl) { b0 = clock64(); if (tid == 128) tl[2] += b0 - c0; }   // conv2 + pool exchange + MLP
     if (is_stream) {
+      // Two groups of three warps take alternate tiles: a tile's publication needs a gpu-scope fence after its stores
+      // (MEMBAR.ALL.GPU + the async-proxy fence: about a store round trip), and with all six warps on every tile that fence
+      // sat on the critical path of every tile (5 900 cycles per tile).  With two groups one group's fence overlaps the
+      // other's loads and arithmetic, and each group issues its next tile's first loads before it fences.
       const int sidx = warp < 4 ? warp - 2 : warp - 10;
-      const int lr = sidx * 4 + (lane >> 3), cg = lane & 7;
+      const int grp = sidx & 1, lr = (sidx >> 1) * 4 + (lane >> 3), cg = lane & 7;
       float s8[8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) { s8[j] = sm_s[cg * 4 + j]; s8[4 + j] = sm_s[32 + cg * 4 + j]; }
       const float* xin = r == 0 ? p.x_in : p.xf;
       const uint16_t* t2 = p.t2_base + (long long)t_idx(r) * p.buf_stride;
       uint16_t* xbo = p.xb_base + (long long)xb_idx(r + 1) * p.buf_stride;
-      constexpr int kU = 6, kStep = kOStream * 4;   // 6 x 24 rows >= one 128-row tile: every load of a tile is in flight at once
+      constexpr int kU = 6, kStep = (kOStream / 2) * 4, kHalf = kU * kStep;   // 2 x 72 rows >= one 128-row tile
       uint2 ta[kU], tc[kU];
       float4 xa[kU], xc[kU];
-      auto issue_loads = [&](int jj) {
+      auto issue_loads = [&](int jj, int h) {
         const int rbase = tile_of(jj) * 128, rend = min(p.RP, rbase + 128);
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-          const int rr = min(rbase + lr + u * kStep, rend - 1);
+          const int rr = min(rbase + h * kHalf + lr + u * kStep, rend - 1);
           const size_t q = (size_t)b * p.RP + rr;
           ta[u] = __ldcg(reinterpret_cast<const uint2*>(t2 + q * 64 + cg * 4));
           tc[u] = __ldcg(reinterpret_cast<const uint2*>(t2 + q * 64 + 32 + cg * 4));
@@ -895,12 +902,11 @@ rcab_chain_ovl_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_con
           xc[u] = __ldcg(reinterpret_cast<const float4*>(xin + q * 64 + 32 + cg * 4));
         }
       };
-      if (n_my > 0) issue_loads(0);
-      for (int jj = 0; jj < n_my; ++jj) {
+      auto update_rows = [&](int jj, int h) {
         const int rbase = tile_of(jj) * 128, rend = min(p.RP, rbase + 128);
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-          const int rr = rbase + lr + u * kStep;
+          const int rr = rbase + h * kHalf + lr + u * kStep;
           if (rr < rend) {
             const size_t q = (size_t)b * p.RP + rr;
             float o[8];
@@ -914,9 +920,13 @@ rcab_chain_ovl_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_con
             __stcg(reinterpret_cast<uint2*>(xbo + q * 64 + 32 + cg * 4), make_uint2(pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7])));
           }
         }
-        // the next tile's loads go out BEFORE this tile's stores are fenced: the two latencies overlap (issued after the
-        // fence, a tile cost load latency + store / fence latency = 5 900 cycles and the six warps needed 59 000 per block)
-        if (jj + 1 < n_my) issue_loads(jj + 1);
+      };
+      if (grp < n_my) issue_loads(grp, 0);
+      for (int jj = grp; jj < n_my; jj += 2) {
+        update_rows(jj, 0);
+        issue_loads(jj, 1);
+        update_rows(jj, 1);
+        if (jj + 2 < n_my) issue_loads(jj + 2, 0);   // in flight while this tile's stores are fenced
         __threadfence();              // this thread's rows are visible gpu-wide ...
         fence_proxy_async_all();      // ... also to the async proxy (TMA loads of this CTA and of the partner)
         __syncwarp();
