@@ -11,9 +11,11 @@
 // RCAB each CTA runs
 //     conv1 (+bias, ReLU -> T1)  |S1|  conv2 (+bias -> T2, channel sums in registers)  |S2|  gate MLP, x += T2 * s  |S3|
 // with the same TMA -> tcgen05 -> TMEM -> TMA-store pipeline as the pair kernel.  S1..S3 are barrier.cluster -- K CTAs, not
-// the grid -- so clusters drift apart freely: one image's streaming phase overlaps other images' tensor-core phases, launch
-// gaps and grid-wide fills / drains disappear, and the grid may be any size (clusters of later waves are independent
-// images).  Weights of the next convolution are prefetched into the region the previous one has finished with; biases,
+// the grid -- so launch gaps and grid-wide fills / drains disappear and the grid may be any size (clusters of later waves
+// are independent images).  (The hope that clusters would drift apart, one image's streaming phase under other images'
+// tensor-core phases, did not come true: equal work keeps them in step, and the phase runs at the 24 B/clk one SM gets out
+// of L2 wherever the others are.  Measured result, DESIGN 3.1c: 642 instead of 1032 launches per training step at the SAME
+// step time; opt-in, SRES_RCAB_CHAIN=1.)  Weights of the next convolution are prefetched into the region the previous one has finished with; biases,
 // squeeze-excite parameters and the saved tensors are addressed by the block index inside the kernel (4-D tensor maps:
 // channel, image row, image, buffer).  Image-local tensor-map coordinates also make the padding work by itself: rows
 // outside [0, (H+1)(W+1)) are zero-filled on load and dropped on store.
